@@ -1,0 +1,145 @@
+"""ctypes binding of libgqb200.so (include/gqb200.h) -- the only way the Python
+classes reach the GPU.  There is no CPU fallback: if the library is missing or a
+call fails, an exception is raised with the library's own error message.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgqb200.so")
+
+c_void_p = ctypes.c_void_p
+c_int = ctypes.c_int
+c_i64 = ctypes.c_int64
+c_u64 = ctypes.c_uint64
+c_size = ctypes.c_size_t
+c_float = ctypes.c_float
+
+ALGO_AUTO, ALGO_EXACT, ALGO_TC = 0, 1, 2
+
+_SIGNATURES = {
+    "gq_abi_version": (c_int, []),
+    "gq_device_info": (c_int, [ctypes.POINTER(c_int)] * 3 + [ctypes.POINTER(c_size)]),
+    "gq_hsq_encode_workspace_bytes": (c_size, [c_i64, c_int, c_int, c_int]),
+    "gq_hsq_encode": (c_int, [c_void_p, c_i64, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
+                              c_void_p, c_u64, c_u64, c_void_p, c_int, c_void_p, c_int, c_void_p,
+                              c_void_p, c_void_p, c_size, c_int, c_void_p]),
+    "gq_hsq_search": (c_int, [c_void_p, c_i64, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p,
+                              c_void_p, c_int, c_void_p, c_void_p, c_size, c_int, c_void_p]),
+    "gq_norm_quantize": (c_int, [c_void_p, c_i64, c_void_p, c_int, c_int, c_int, c_void_p, c_u64, c_u64,
+                                 c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    "gq_norm_dequantize": (c_int, [c_void_p, c_int, c_i64, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                   c_void_p]),
+    "gq_hsq_decode_reduce": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_i64, c_int,
+                                     c_i64, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
+                                     c_void_p, c_void_p]),
+    "gq_f32_reduce_users": (c_int, [c_void_p, c_i64, c_int, c_i64, c_int, c_int, c_void_p, c_void_p]),
+    "gq_qsgd_wire_bits": (c_int, [c_int]),
+    "gq_qsgd_encode": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_int, c_int, c_int, c_void_p, c_u64,
+                               c_u64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "gq_qsgd_decode_reduce": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_i64, c_void_p, c_i64, c_int,
+                                      c_int, c_int, c_int, c_void_p, c_void_p]),
+    "gq_qsgd_decode_unpacked": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_int, c_int,
+                                        c_void_p, c_void_p]),
+    "gq_sign_encode": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_void_p]),
+    "gq_sign_decode_reduce": (c_int, [c_void_p, c_i64, c_int, c_i64, c_int, c_int, c_void_p, c_void_p]),
+    "gq_topk_workspace_bytes": (c_size, [c_i64, c_int]),
+    "gq_topk_select": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                               c_void_p, c_void_p, c_size, c_void_p]),
+    "gq_topk_scatter_reduce": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_i64, c_i64, c_int, c_int,
+                                       c_void_p, c_void_p]),
+    "gq_pvc_search": (c_int, [c_void_p, c_i64, c_int, c_void_p, c_int, c_void_p, c_u64, c_u64, c_void_p,
+                              c_int, c_void_p, c_void_p]),
+    "gq_axpy": (c_int, [c_void_p, c_void_p, c_float, c_i64, c_void_p, c_void_p]),
+    "gq_sub": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_void_p]),
+    "gq_hsq_host_scratch_bytes": (c_size, [c_i64, c_int, c_int, c_int]),
+    "gq_hsq_roundtrip_host": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p, c_int, c_void_p, c_int,
+                                      c_int, c_int, c_u64, c_u64, c_void_p, c_size, c_int, c_void_p]),
+}
+
+EXPORTS = ["gq_last_error"] + sorted(_SIGNATURES)
+
+_lib = None
+
+
+class GQError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "libgqb200.so is missing (%s). Build it with `python gradient-quantization_b200/build.py` "
+            "or __graft_entry__.build(); there is no CPU fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.gq_last_error.restype = ctypes.c_char_p
+    lib.gq_last_error.argtypes = []
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    """Call an int-returning entry point; raise GQError on a non-zero status."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise GQError("%s failed (%d): %s" % (name, rc, lib.gq_last_error().decode()))
+
+
+def value(name, *args):
+    return getattr(load(), name)(*args)
+
+
+# ------------------------------------------------------------ torch glue ---
+def require_cuda(t, what="tensor"):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise GQError("%s must be a CUDA tensor: this implementation has no CPU path" % what)
+    return t
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def f32c(t, what="tensor"):
+    """fp32, contiguous, CUDA view of t (copies only when it must)."""
+    require_cuda(t, what)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+class PhiloxState:
+    """Seed/offset bookkeeping for the on-device Philox stream: the seed follows
+    torch.manual_seed, the offset advances by the number of uniforms each call
+    consumes, so runs are reproducible for a fixed call sequence."""
+
+    def __init__(self):
+        self._seed = None
+        self.offset = 0
+
+    def take(self, n):
+        seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
+        if seed != self._seed:
+            self._seed, self.offset = seed, 0
+        off = self.offset
+        self.offset += (int(n) + 3) // 4 * 4
+        return seed, off
+
+
+PHILOX = PhiloxState()

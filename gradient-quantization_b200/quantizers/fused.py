@@ -1,0 +1,354 @@
+"""Whole-model fused codec plan: the engine under PSQuantizer / RingQuantizer.
+
+The reference loops over parameters and calls compress()/decompress() per tensor
+(quantizers/ps_quantizer.py:33-44); on a B200 that is ~160 tiny launches per
+user.  Here the parameters are grouped by codec shape once, their gradients are
+staged in one flat fp32 *arena* (group by group, tensors end to end), and each
+user's compressed form is one contiguous *packed record*:
+
+    record = [ per HSQ group : codes | l (or fp32 norms) | lb/ub table ]
+             [ per QSGD group: chunk norms | packed sign+level          ]
+             [ sign group    : 2-bit packed signs                       ]
+             [ top-k group   : int32 indices | fp32 values              ]
+             [ identity      : raw fp32 (tensors with <= 1000 elements) ]
+
+records is a [U, record_bytes] uint8 buffer -- exactly the receive buffer of an
+NCCL all-gather with one user per rank -- and decode is one fused
+decode-and-reduce launch per group over all U records, in user order.
+Every section starts on a 256-byte boundary.
+"""
+import torch
+
+from .. import _lib
+from ..compressors import (IdenticalCompressor, NearestNeighborCompressor, QSGDCompressor,
+                           SignSGDCompressor, TopKSparsificationCompressor)
+from ..compressors._common import chunk_dim, load_codebook
+
+_ALIGN = 256
+
+
+def _up(x, a=_ALIGN):
+    return (x + a - 1) // a * a
+
+
+class _Group:
+    """A set of tensors sharing one codec configuration, contiguous in the arena."""
+
+    def __init__(self, kind, key):
+        self.kind, self.key = kind, key
+        self.tensors = []      # indices into plan.shapes
+        self.sizes = []
+        self.arena_off = 0     # element offset of the group in the arena
+        self.n = 0             # elements
+
+    def add(self, idx, size):
+        self.tensors.append(idx)
+        self.sizes.append(size)
+        self.n += size
+
+
+class FusedPlan:
+    SUPPORTED = (NearestNeighborCompressor, QSGDCompressor, SignSGDCompressor,
+                 TopKSparsificationCompressor, IdenticalCompressor)
+
+    @classmethod
+    def supports(cls, Compressor):
+        return Compressor in cls.SUPPORTED
+
+    def __init__(self, Compressor, shapes, args, device, n_users):
+        self.Compressor = Compressor
+        self.shapes = [tuple(s) for s in shapes]
+        self.sizes = [int(torch.Size(s).numel()) for s in self.shapes]
+        self.args = args
+        self.device = device
+        self.n_users = n_users
+        self.random = 1 if getattr(args, "random", True) else 0
+        self.algo = getattr(args, "hsq_algo", _lib.ALGO_AUTO)
+        self.groups = []
+        self._classify()
+        self._layout()
+        self.arena = torch.zeros(self.arena_elems, dtype=torch.float32, device=device)
+        self.records = torch.zeros(n_users, self.record_bytes, dtype=torch.uint8, device=device)
+        self.workspace = torch.empty(max(self.workspace_bytes, _ALIGN), dtype=torch.uint8, device=device)
+        self.u_scratch = torch.empty(max(self.max_chunks, 1), dtype=torch.float32, device=device)
+
+    # ------------------------------------------------------------ planning ---
+    def _classify(self):
+        a = self.args
+        by_key = {}
+        order = []
+
+        def group(kind, key):
+            if (kind, key) not in by_key:
+                by_key[(kind, key)] = _Group(kind, key)
+                order.append((kind, key))
+            return by_key[(kind, key)]
+
+        self.tensor_group = []
+        for i, size in enumerate(self.sizes):
+            # the reference compresses only tensors with more than 1000 elements
+            # (ps_quantizer.py:15-20)
+            if size <= 1000 or self.Compressor is IdenticalCompressor:
+                g = group("identity", None)
+            elif self.Compressor is NearestNeighborCompressor:
+                assert a.c_dim > 0 and a.k_bit >= 0 and a.n_bit > 0
+                dim = chunk_dim(size, a.c_dim)
+                assert size % dim == 0, "not divisible size {} c_dim {} dim {}".format(size, a.c_dim, dim)
+                K = dim if a.k_bit <= 0 else 2 ** a.k_bit
+                if K == dim:
+                    raise _lib.GQError("fused plan: random orthogonal codebooks (K == dim) are per-tensor; "
+                                       "use the per-parameter path")
+                g = group("hsq", (dim, K))
+            elif self.Compressor is QSGDCompressor:
+                dim = chunk_dim(size, a.c_dim)
+                assert dim != 0 and size % dim == 0
+                g = group("qsgd", "tensor" if (a.c_dim == 0 or size < a.c_dim) else dim)
+            elif self.Compressor is SignSGDCompressor:
+                g = group("sign", None)
+            elif self.Compressor is TopKSparsificationCompressor:
+                g = group("topk", None)
+            else:
+                raise _lib.GQError("fused plan does not support %r" % (self.Compressor,))
+            g.add(i, size)
+            self.tensor_group.append(g)
+        # identity last, compressed groups in first-appearance order
+        self.groups = [by_key[k] for k in order if k[0] != "identity"]
+        self.groups += [by_key[k] for k in order if k[0] == "identity"]
+
+    def _layout(self):
+        a = self.args
+        dev = self.device
+        off_el = 0
+        rec = 0
+        ws = 0
+        self.max_chunks = 0
+        self.tensor_off = [0] * len(self.sizes)
+        for g in self.groups:
+            off_el = _up(off_el * 4) // 4
+            g.arena_off = off_el
+            t_off = off_el
+            for idx, size in zip(g.tensors, g.sizes):
+                self.tensor_off[idx] = t_off
+                t_off += size
+            off_el += g.n
+            if g.kind == "hsq":
+                dim, K = g.key
+                g.dim, g.K = dim, K
+                g.n_chunks = g.n // dim
+                g.n_seg = len(g.tensors)
+                starts = [0]
+                for size in g.sizes:
+                    starts.append(starts[-1] + size // dim)
+                g.seg_start = torch.tensor(starts, dtype=torch.int64, device=dev)
+                g.seg_start_host = starts
+                g.codebook = torch.from_numpy(load_codebook(dim, K)).to(dev)
+                g.code_bytes = 1 if a.k_bit <= 8 else 4
+                g.n_bit = a.n_bit
+                g.l_bytes = 1 if a.n_bit <= 7 else 4
+                g.codes_off = rec
+                rec += _up(g.n_chunks * g.code_bytes)
+                g.l_off = rec                       # l codes, or fp32 norms when n_bit == 32
+                rec += _up(g.n_chunks * (4 if a.n_bit == 32 else g.l_bytes))
+                g.lbub_off = rec
+                rec += _up(g.n_seg * 8)
+                ws = max(ws, _lib.value("gq_hsq_encode_workspace_bytes", g.n_chunks, dim, K, g.n_seg))
+                self.max_chunks = max(self.max_chunks, g.n_chunks)
+            elif g.kind == "qsgd":
+                g.n_bit = a.n_bit
+                g.bits = _lib.value("gq_qsgd_wire_bits", a.n_bit)
+                if g.key == "tensor":       # one chunk per tensor (TernGrad, c_dim == 0)
+                    g.dim = 0
+                    g.n_chunks = len(g.tensors)
+                    starts = [0]
+                    for size in g.sizes:
+                        starts.append(starts[-1] + size)
+                    g.chunk_start = torch.tensor(starts, dtype=torch.int64, device=dev)
+                else:
+                    g.dim = g.key
+                    g.n_chunks = g.n // g.dim
+                    g.chunk_start = None
+                g.norm_off = rec
+                rec += _up(g.n_chunks * 4)
+                g.packed_off = rec
+                rec += _up((g.n + 3) // 4 * 4 * g.bits // 8)
+            elif g.kind == "sign":
+                g.packed_off = rec
+                rec += _up((g.n + 3) // 4)
+            elif g.kind == "topk":
+                g.n_seg = len(g.tensors)
+                starts, ks, kp = [0], [], [0]
+                for size in g.sizes:
+                    starts.append(starts[-1] + size)
+                    ks.append(size // a.cr)
+                    kp.append(kp[-1] + ks[-1])
+                g.k_total = kp[-1]
+                g.seg_start = torch.tensor(starts, dtype=torch.int64, device=dev)
+                g.k = torch.tensor(ks, dtype=torch.int64, device=dev)
+                g.k_prefix = torch.tensor(kp[:-1], dtype=torch.int64, device=dev)
+                g.idx_off = rec
+                rec += _up(g.k_total * 4)
+                g.val_off = rec
+                rec += _up(g.k_total * 4)
+                ws = max(ws, _lib.value("gq_topk_workspace_bytes", g.n, g.n_seg))
+            elif g.kind == "identity":
+                g.raw_off = rec
+                rec += _up(g.n * 4)
+        self.arena_elems = _up(off_el * 4) // 4
+        self.record_bytes = _up(rec)
+        self.workspace_bytes = ws
+
+    # --------------------------------------------------------------- views ---
+    def view(self, i, buf=None):
+        """View of tensor i inside the arena (or another buffer laid out like it)."""
+        buf = self.arena if buf is None else buf
+        o = self.tensor_off[i]
+        return buf[o:o + self.sizes[i]].view(self.shapes[i])
+
+    def views(self, buf=None):
+        return [self.view(i, buf) for i in range(len(self.sizes))]
+
+    def gather(self, tensors, buf=None):
+        """Copy per-parameter gradients into the arena (skips views already in it)."""
+        dst, src = [], []
+        for i, t in enumerate(tensors):
+            v = self.view(i, buf)
+            if t.data_ptr() != v.data_ptr():
+                dst.append(v)
+                src.append(t.detach().reshape(self.shapes[i]))
+        if dst:
+            torch._foreach_copy_(dst, src)
+
+    def compressed_elems(self):
+        return sum(g.n for g in self.groups if g.kind != "identity")
+
+    def total_elems(self):
+        return sum(self.sizes)
+
+    def wire_bytes(self):
+        """Useful (unpadded) bytes of one packed record."""
+        b = 0
+        for g in self.groups:
+            if g.kind == "hsq":
+                b += g.n_chunks * g.code_bytes + g.n_chunks * (4 if g.n_bit == 32 else g.l_bytes) + g.n_seg * 8
+            elif g.kind == "qsgd":
+                b += g.n_chunks * 4 + (g.n * g.bits + 7) // 8
+            elif g.kind == "sign":
+                b += (g.n + 3) // 4
+            elif g.kind == "topk":
+                b += g.k_total * 8
+            else:
+                b += g.n * 4
+        return b
+
+    # ------------------------------------------------------------- uniforms ---
+    def split_uniform_stream(self, stream, skip=()):
+        """Cut a flat uniform stream drawn in the reference's call order (tensor by
+        tensor: rand(N/d) per HSQ tensor, rand(size) per QSGD tensor; tensors in
+        `skip` consume nothing) into one device array per group."""
+        per_group = {id(g): [] for g in self.groups}
+        pos = 0
+        for i, g in enumerate(self.tensor_group):
+            if g.kind == "hsq":
+                n = self.sizes[i] // g.dim
+            elif g.kind == "qsgd":
+                n = self.sizes[i]
+            else:
+                continue
+            if i in skip:
+                chunk = torch.zeros(n, dtype=torch.float32)
+            else:
+                chunk = torch.as_tensor(stream[pos:pos + n], dtype=torch.float32)
+                assert chunk.numel() == n, "uniform stream exhausted"
+                pos += n
+            per_group[id(g)].append(chunk)
+        out = {}
+        for g in self.groups:
+            if per_group[id(g)]:
+                out[id(g)] = torch.cat(per_group[id(g)]).to(self.device)
+        return out, pos
+
+    # --------------------------------------------------------------- encode ---
+    def encode(self, user, src=None, uniforms=None):
+        """Compress the arena (or `src`, laid out like it) into records[user].
+        Launches: HSQ 3 per group (init, search, quantize), QSGD 3, sign 1, top-k 12, identity 1."""
+        src = self.arena if src is None else src
+        rec = self.records[user]
+        st = _lib.stream()
+        base = rec.data_ptr()
+        for g in self.groups:
+            gp = src.data_ptr() + g.arena_off * 4
+            r = None if uniforms is None else uniforms.get(id(g))
+            if g.kind == "hsq":
+                n_rand = g.n_chunks if (self.random and g.n_bit != 32) else 0
+                seed, off = _lib.PHILOX.take(n_rand) if (n_rand and r is None) else (0, 0)
+                if g.n_bit == 32:
+                    _lib.call("gq_hsq_encode", gp, g.n_chunks, g.dim, _lib.ptr(g.codebook), g.K,
+                              _lib.ptr(g.seg_start), g.n_seg, 32, 0, None, 0, 0, base + g.codes_off,
+                              g.code_bytes, None, 4, None, base + g.l_off, _lib.ptr(self.workspace),
+                              self.workspace.numel(), self.algo, st)
+                else:
+                    _lib.call("gq_hsq_encode", gp, g.n_chunks, g.dim, _lib.ptr(g.codebook), g.K,
+                              _lib.ptr(g.seg_start), g.n_seg, g.n_bit, self.random, _lib.ptr(r), seed, off,
+                              base + g.codes_off, g.code_bytes, base + g.l_off, g.l_bytes,
+                              base + g.lbub_off, _lib.ptr(self.u_scratch), _lib.ptr(self.workspace),
+                              self.workspace.numel(), self.algo, st)
+            elif g.kind == "qsgd":
+                seed, off = _lib.PHILOX.take(g.n) if (self.random and r is None) else (0, 0)
+                _lib.call("gq_qsgd_encode", gp, g.n, _lib.ptr(g.chunk_start), g.n_chunks, g.dim, g.n_bit,
+                          self.random, _lib.ptr(r), seed, off, base + g.norm_off, None, None,
+                          base + g.packed_off, st)
+            elif g.kind == "sign":
+                _lib.call("gq_sign_encode", gp, g.n, None, base + g.packed_off, st)
+            elif g.kind == "topk":
+                _lib.call("gq_topk_select", gp, g.n, _lib.ptr(g.seg_start), _lib.ptr(g.k),
+                          _lib.ptr(g.k_prefix), g.n_seg, None, base + g.idx_off, base + g.val_off,
+                          _lib.ptr(self.workspace), self.workspace.numel(), st)
+            elif g.kind == "identity":
+                if g.n:
+                    rec[g.raw_off:g.raw_off + g.n * 4].view(torch.float32).copy_(
+                        src[g.arena_off:g.arena_off + g.n])
+
+    # --------------------------------------------------------------- decode ---
+    def decode(self, first_user=0, n_users=None, mean=True, accumulate=False, out=None):
+        """out (arena layout) = [out +] reduce over records[first_user : first_user+n_users]."""
+        out = self.arena if out is None else out
+        n_users = self.n_users if n_users is None else n_users
+        st = _lib.stream()
+        base = self.records.data_ptr() + first_user * self.record_bytes
+        stride = self.record_bytes
+        mean = 1 if mean else 0
+        acc = 1 if accumulate else 0
+        for g in self.groups:
+            op = out.data_ptr() + g.arena_off * 4
+            if g.kind == "hsq":
+                if g.n_bit == 32:
+                    _lib.call("gq_hsq_decode_reduce", base + g.codes_off, g.code_bytes, None, 1, None,
+                              base + g.l_off, stride, n_users, g.n_chunks, g.dim, _lib.ptr(g.codebook), g.K,
+                              _lib.ptr(g.seg_start), g.n_seg, 32, mean, acc, op, st)
+                else:
+                    _lib.call("gq_hsq_decode_reduce", base + g.codes_off, g.code_bytes, base + g.l_off,
+                              g.l_bytes, base + g.lbub_off, None, stride, n_users, g.n_chunks, g.dim,
+                              _lib.ptr(g.codebook), g.K, _lib.ptr(g.seg_start), g.n_seg, g.n_bit, mean,
+                              acc, op, st)
+            elif g.kind == "qsgd":
+                _lib.call("gq_qsgd_decode_reduce", base + g.norm_off, base + g.packed_off, stride, n_users,
+                          g.n, _lib.ptr(g.chunk_start), g.n_chunks, g.dim, g.n_bit, mean, acc, op, st)
+            elif g.kind == "sign":
+                _lib.call("gq_sign_decode_reduce", base + g.packed_off, stride, n_users, g.n, mean, acc,
+                          op, st)
+            elif g.kind == "topk":
+                _lib.call("gq_topk_scatter_reduce", base + g.idx_off, base + g.val_off, stride, n_users,
+                          g.k_total, g.n, mean, acc, op, st)
+            elif g.kind == "identity":
+                _lib.call("gq_f32_reduce_users", base + g.raw_off, stride, n_users, g.n, mean, acc, op, st)
+        return out
+
+    def launches_per_encode(self):
+        per = {"hsq": 3, "qsgd": 3, "sign": 1, "topk": 12, "identity": 1}
+        return sum(per[g.kind] - (1 if (g.kind == "hsq" and g.n_bit == 32) else 0) for g in self.groups)
+
+    def launches_per_decode(self, n_users):
+        n = 0
+        for g in self.groups:
+            n += (2 + n_users) if g.kind == "topk" else 1
+        return n

@@ -1,0 +1,76 @@
+import torch
+import torch.distributed as dist
+
+from .. import _lib
+from ._shared import QuantizerBase, feedback_scale
+
+
+class RingQuantizer(QuantizerBase):
+    """Ring exchange (reference quantizers/ring_quantizer.py:7-49): a lossy running
+    SUM passed from user to user, acc_r = D(C(g_r + acc_{r-1})); apply() hands the
+    last user's decompressed sum (not divided by the number of users) to every
+    parameter.
+
+    Fused path: record(user) decodes records[user-1] straight into the gradient
+    arena (decode-accumulate), then packs the sum into records[user].  With one
+    user per rank the packed record travels rank r -> r+1 with NCCL send/recv and
+    the last rank broadcasts its record; fp32 never crosses NVLink.
+    """
+
+    def __init__(self, Compressor, parameters, args):
+        super().__init__(Compressor, parameters, args)
+
+    def record(self, user, epoch, uniforms=None):
+        scale = feedback_scale(self.args, epoch)
+        if self.plan is None:
+            return self._record_per_parameter(user, scale)
+        plan = self.plan
+        if self.distributed and user != self.rank:
+            raise _lib.GQError("distributed mode: rank %d records user %d only" % (self.rank, self.rank))
+        plan.gather(self._grads())
+        if user != 0:
+            if self.distributed:
+                dist.recv(plan.records[user - 1], src=user - 1)
+            # grad += previous hop's decompressed running sum   (ring_quantizer.py:31-32)
+            plan.decode(first_user=user - 1, n_users=1, mean=False, accumulate=True, out=plan.arena)
+        n = plan.arena.numel()
+        if self.error_feedback:
+            err = self._ef_buffers(user)
+            _lib.call("gq_axpy", _lib.ptr(plan.arena), _lib.ptr(err), float(scale), n,
+                      _lib.ptr(plan.arena), _lib.stream())
+        plan.encode(user, uniforms=uniforms)
+        if self.error_feedback:
+            if not hasattr(self, "_scratch_buf"):
+                self._scratch_buf = torch.empty_like(plan.arena)
+            dec = plan.decode(first_user=user, n_users=1, mean=False, out=self._scratch_buf)
+            _lib.call("gq_sub", _lib.ptr(plan.arena), _lib.ptr(dec), n, _lib.ptr(err), _lib.stream())
+        if self.distributed and user + 1 < self.world:
+            dist.send(plan.records[user], dst=user + 1)
+
+    def _record_per_parameter(self, user, scale):
+        for i, param in enumerate(self.parameters):
+            if user != 0:
+                param.grad.data.add_(self.compressed_gradients[i][-1])
+            if self.error_feedback:
+                param.grad.data.add_(scale * param.error[user])
+                decompressed_g = self.compressors[i].decompress(
+                    self.compressors[i].compress(param.grad.data))
+                param.error[user].data = param.grad.data - decompressed_g
+            else:
+                decompressed_g = self.compressors[i].decompress(
+                    self.compressors[i].compress(param.grad.data))
+            self.compressed_gradients[i].append(decompressed_g)
+
+    def apply(self):
+        if self.plan is None:
+            for i, param in enumerate(self.parameters):
+                param.grad.data = self.compressed_gradients[i][-1]
+            for compressed in self.compressed_gradients:
+                compressed.clear()
+            return
+        plan = self.plan
+        last = self.args.num_users - 1
+        if self.distributed:
+            dist.broadcast(plan.records[last], src=last)
+        g = plan.decode(first_user=last, n_users=1, mean=False, out=plan.arena)
+        self._set_grads_from(g)

@@ -1,0 +1,229 @@
+/*
+ * gqb200.h -- C ABI of libgqb200.so, the B200 (sm_100a) implementation of the
+ * gradient-compression hot path of xinyandai/gradient-quantization.
+ *
+ * Boundary rules
+ *   - extern "C", plain pointers and sizes, no torch / C++ types.
+ *   - every pointer marked "device" is a CUDA device pointer on the current
+ *     device; "host" pointers are ordinary (preferably pinned) host memory.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*)
+ *     unless it says otherwise; no call allocates device memory: the caller
+ *     supplies outputs and the workspace (size from gq_*_workspace_bytes).
+ *   - return value: 0 = GQ_OK, otherwise a GQ_ERR_* code; gq_last_error()
+ *     returns a thread-local, human-readable message for the last failure.
+ *   - there is no CPU fallback: without a usable sm_100 device the calls fail
+ *     with GQ_ERR_CUDA.
+ *
+ * Each entry point cites the reference interface it replaces (file:line,
+ * relative to the reference checkout).  The Python classes of the same names as
+ * the reference's (gradient-quantization_b200/compressors, quantizers) are thin
+ * ctypes callers of these functions; INTEGRATION.md shows the binding.
+ *
+ * Data layout ("packed record", one per simulated user / rank)
+ *   chunk matrix : fp32 [n_chunks, d] row-major = the gradient tensors of one
+ *                  codec group laid end to end (every tensor a multiple of d).
+ *   seg_start    : int64 [n_seg + 1], chunk index where tensor s starts;
+ *                  seg_start[n_seg] == n_chunks.  Per-tensor quantities
+ *                  (lb/ub of the norm quantizer) are indexed by s.
+ *   codes        : uint8 [n_chunks] (K <= 256) or int32 [n_chunks]
+ *   l            : uint8 [n_chunks] (wire) or int32 [n_chunks] (reference dtype)
+ *   lbub         : fp32 [2 * n_seg] = (lb_0, ub_0, lb_1, ub_1, ...)
+ */
+#ifndef GQB200_H
+#define GQB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GQ_OK 0
+#define GQ_ERR_INVALID 1     /* bad argument (message says which)            */
+#define GQ_ERR_CUDA 2        /* CUDA runtime/driver error, or no sm_100 GPU   */
+#define GQ_ERR_UNSUPPORTED 3 /* valid request this build has no kernel for    */
+#define GQ_ERR_WORKSPACE 4   /* workspace too small                           */
+
+/* HSQ search algorithm selector */
+#define GQ_ALGO_AUTO 0   /* tcgen05 path when (d, K) allow it, else exact CUDA-core */
+#define GQ_ALGO_EXACT 1  /* fp32 CUDA-core search (any d <= 64, any K)              */
+#define GQ_ALGO_TC 2     /* tcgen05 TF32 search + fp32 rescoring (d == 16, K == 256) */
+
+typedef void *gq_stream_t; /* cudaStream_t */
+
+const char *gq_last_error(void);
+int gq_abi_version(void);
+/* device facts used by the host code to size grids/workspaces; synchronous. */
+int gq_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *total_mem);
+
+/* ------------------------------------------------------------------------- */
+/* HSQ encode: nearest-codeword search + n-bit norm quantization.
+ * Replaces NearestNeighborCompressor.compress
+ *   (compressors/nearest_neighbor_compressor.py:63-78) and the
+ *   ProbabilisticScalarCompressor.compress it calls
+ *   (compressors/probabilistic_scalar_compressor.py:12-27), for a whole group
+ *   of tensors in one call (the per-parameter loop of
+ *   quantizers/ps_quantizer.py:33-44).
+ *
+ * grad      device fp32 [n_chunks*d]   chunk matrix (16-byte aligned)
+ * codebook  device fp32 [K*d]          unit-norm rows, row-major
+ * seg_start device int64 [n_seg+1]
+ * n_bit     norm bits; 32 = keep fp32 norms (u_out is then the result, l/lbub untouched)
+ * random    0: truncate, 1: stochastic rounding (l += (frac > r))
+ * uniforms  device fp32 [n_chunks] of U[0,1) draws indexed by chunk, or NULL to
+ *           use the built-in Philox4x32-10 stream (philox_seed, philox_offset + chunk)
+ * codes     device out, code_bytes in {1, 4}  (1 requires K <= 256)
+ * l         device out, l_bytes in {1, 4}     (values 0..2^n_bit; 1 requires n_bit <= 7)
+ * lbub      device out fp32 [2*n_seg]
+ * u_out     device out fp32 [n_chunks]: signed projection of every chunk
+ * bit-exactness: codes, u, lb/ub and (given the same uniforms) l equal the
+ * reference's CPU result bit for bit (sequential ascending-j fp32 FMA chain,
+ * first index wins ties).
+ */
+size_t gq_hsq_encode_workspace_bytes(int64_t n_chunks, int d, int K, int n_seg);
+int gq_hsq_encode(const float *grad, int64_t n_chunks, int d,
+                  const float *codebook, int K,
+                  const int64_t *seg_start, int n_seg,
+                  int n_bit, int random, const float *uniforms,
+                  uint64_t philox_seed, uint64_t philox_offset,
+                  void *codes, int code_bytes, void *l, int l_bytes,
+                  float *lbub, float *u_out,
+                  void *workspace, size_t workspace_bytes, int algo, gq_stream_t stream);
+
+/* The two halves of gq_hsq_encode, exposed because the reference exposes them
+ * as separate classes (ResidualCompressor / PVC reuse the norm quantizer). */
+int gq_hsq_search(const float *grad, int64_t n_chunks, int d, const float *codebook, int K,
+                  void *codes, int code_bytes, float *u_out,
+                  const int64_t *seg_start, int n_seg, uint32_t *minmax_keys /* [2*n_seg] or NULL */,
+                  void *workspace, size_t workspace_bytes, int algo, gq_stream_t stream);
+
+/* ProbabilisticScalarCompressor.compress (probabilistic_scalar_compressor.py:12-27)
+ * over every segment of u: per-segment lb/ub, then l.  minmax_keys is scratch
+ * [2*n_seg] uint32 (filled here when precomputed == 0). */
+int gq_norm_quantize(const float *u, int64_t n, const int64_t *seg_start, int n_seg,
+                     int n_bit, int random, const float *uniforms,
+                     uint64_t philox_seed, uint64_t philox_offset,
+                     void *l, int l_bytes, float *lbub,
+                     uint32_t *minmax_keys, int precomputed, gq_stream_t stream);
+
+/* ProbabilisticScalarCompressor.decompress (probabilistic_scalar_compressor.py:29-33):
+ * out[i] = l[i] * (ub - lb) / 2^n_bit + lb. */
+int gq_norm_dequantize(const void *l, int l_bytes, int64_t n, const int64_t *seg_start, int n_seg,
+                       int n_bit, const float *lbub, float *out, gq_stream_t stream);
+
+/* ------------------------------------------------------------------------- */
+/* HSQ decode-and-reduce over users.
+ * Replaces NearestNeighborCompressor.decompress
+ *   (compressors/nearest_neighbor_compressor.py:80-90) +
+ *   ProbabilisticScalarCompressor.decompress (probabilistic_scalar_compressor.py:29-33)
+ *   for U users and the stack(...).mean(0) of PSQuantizer.apply
+ *   (quantizers/ps_quantizer.py:48), or the `grad += previous` of
+ *   RingQuantizer.record (quantizers/ring_quantizer.py:31-32).
+ *
+ * User u's arrays live at codes + u*user_stride_bytes, l + u*user_stride_bytes,
+ * (char*)lbub + u*user_stride_bytes (the all-gathered packed records); when
+ * n_bit == 32, `l` is unused and norms_f32 (+ u*user_stride_bytes) holds fp32 norms.
+ *   r[i]   = sum_{u=0..U-1} codebook[code_u[c], j] * norm_u[c]   (user order)
+ *   mean   : r /= U                 (true division)
+ *   out[i] = accumulate ? out[i] + r[i] : r[i]
+ */
+int gq_hsq_decode_reduce(const void *codes, int code_bytes, const void *l, int l_bytes,
+                         const float *lbub, const float *norms_f32,
+                         int64_t user_stride_bytes, int n_users,
+                         int64_t n_chunks, int d, const float *codebook, int K,
+                         const int64_t *seg_start, int n_seg, int n_bit,
+                         int mean, int accumulate, float *out, gq_stream_t stream);
+
+/* out[i] = (sum_u in[u*user_stride_bytes + 4*i]) / U (mean) -- identity tensors
+ * (compressors/identical_compressor.py:5-11 under ps_quantizer.py:48). */
+int gq_f32_reduce_users(const float *in, int64_t user_stride_bytes, int n_users, int64_t n,
+                        int mean, int accumulate, float *out, gq_stream_t stream);
+
+/* ------------------------------------------------------------------------- */
+/* QSGD / TernGrad.  Replaces QSGDCompressor.compress / decompress
+ *   (compressors/qsgd_compressor.py:42-64, 66-71).
+ * grad fp32 [n_chunks*dim]; norm out fp32 [n_chunks] (L-inf per chunk).
+ * unpacked outputs (reference dtypes): signs uint8 [n] (0/1), l int32 [n]
+ *   (an all-zero chunk yields INT32_MIN like the reference's NaN cast).
+ * packed output (wire): bits_per_elem in {4, 8, 16}: (sign << (bits-1)) | l.
+ * Either `packed` or both `signs` and `l` may be NULL.
+ * uniforms: device fp32 [n] or NULL for Philox. */
+int gq_qsgd_wire_bits(int n_bit);
+/* n = total elements.  Chunks are either uniform (chunk_start == NULL,
+ * n == n_chunks*dim) or variable (chunk_start int64 [n_chunks+1] on the device,
+ * e.g. one chunk per tensor for TernGrad's c_dim == 0; dim ignored). */
+int gq_qsgd_encode(const float *grad, int64_t n, const int64_t *chunk_start, int64_t n_chunks, int dim,
+                   int n_bit, int random, const float *uniforms, uint64_t philox_seed,
+                   uint64_t philox_offset, float *norm, uint8_t *signs, int32_t *l, void *packed,
+                   gq_stream_t stream);
+/* decode-and-reduce over users from the packed wire format
+ * (qsgd_compressor.py:66-71 + ps_quantizer.py:48 / ring_quantizer.py:31-32);
+ * user u's norm / packed arrays are at + u*user_stride_bytes. */
+int gq_qsgd_decode_reduce(const float *norm, const void *packed, int64_t user_stride_bytes, int n_users,
+                          int64_t n, const int64_t *chunk_start, int64_t n_chunks, int dim, int n_bit,
+                          int mean, int accumulate, float *out, gq_stream_t stream);
+/* decode one user from the unpacked (reference-dtype) signature */
+int gq_qsgd_decode_unpacked(const float *norm, const uint8_t *signs, const int32_t *l, int64_t n,
+                            const int64_t *chunk_start, int64_t n_chunks, int dim, int n_bit, float *out,
+                            gq_stream_t stream);
+
+/* ------------------------------------------------------------------------- */
+/* SignSGD.  Replaces SignSGDCompressor.compress (compressors/signsgd_compressor.py:8-9).
+ * out_f32 (reference dtype, {-1,0,+1}) and/or packed (2 bits/elem, 4 per byte:
+ * 0 -> 0, 1 -> +1, 2 -> -1; n rounded up to a multiple of 4). */
+int gq_sign_encode(const float *grad, int64_t n, float *out_f32, uint8_t *packed, gq_stream_t stream);
+int gq_sign_decode_reduce(const uint8_t *packed, int64_t user_stride_bytes, int n_users, int64_t n,
+                          int mean, int accumulate, float *out, gq_stream_t stream);
+
+/* ------------------------------------------------------------------------- */
+/* Top-k sparsification.  Replaces TopKSparsificationCompressor.compress
+ *   (compressors/topk_sparsification_compressor.py:18-23): per tensor
+ *   (segment) keep the k_s largest |v| (ties at the cut: lowest index first),
+ *   zero the rest.
+ * seg_start int64 [n_seg+1] in ELEMENTS; k int64 [n_seg] (both device).
+ * out_dense (reference form, vec*mask incl. signed zeros) may be NULL;
+ * out_idx int32 [sum k] / out_val fp32 [sum k] (wire form, ascending index
+ * inside each segment, segment s at offset k_prefix[s]) may be NULL. */
+size_t gq_topk_workspace_bytes(int64_t n, int n_seg);
+int gq_topk_select(const float *grad, int64_t n, const int64_t *seg_start, const int64_t *k,
+                   const int64_t *k_prefix, int n_seg, float *out_dense, int32_t *out_idx,
+                   float *out_val, void *workspace, size_t workspace_bytes, gq_stream_t stream);
+/* out = [accumulate? out : 0] + sum over users (user order) of the sparse entries, / U if mean.
+ * idx are GLOBAL element indices (seg_start[s] + local index). */
+int gq_topk_scatter_reduce(const int32_t *idx, const float *val, int64_t user_stride_bytes,
+                           int n_users, int64_t k_total, int64_t n, int mean, int accumulate,
+                           float *out, gq_stream_t stream);
+
+/* ------------------------------------------------------------------------- */
+/* Probabilistic vector compressor search (INTENDED semantics of
+ *   compressors/probabilistic_vector_compressor.py:42-65; the shipped class does
+ *   not run -- DESIGN.md "PVC").  dagger = pinv(C^T) fp32 [K*d] row-major.
+ *   code = first k with cumsum(|p|/l1)_k >= r - 1e-5 ; u = sign(p_code) * l1.
+ * uniforms: device fp32 [n_chunks] or NULL for Philox. */
+int gq_pvc_search(const float *grad, int64_t n_chunks, int d, const float *dagger, int K,
+                  const float *uniforms, uint64_t philox_seed, uint64_t philox_offset,
+                  void *codes, int code_bytes, float *u_out, gq_stream_t stream);
+
+/* ------------------------------------------------------------------------- */
+/* Elementwise helpers the quantizers need around the codecs.
+ * out = a + alpha*b  (ps_quantizer.py:35 error feedback; ring_quantizer.py:32)
+ * out = a - b        (ps_quantizer.py:39; residual_compressor.py:21) */
+int gq_axpy(const float *a, const float *b, float alpha, int64_t n, float *out, gq_stream_t stream);
+int gq_sub(const float *a, const float *b, int64_t n, float *out, gq_stream_t stream);
+
+/* ------------------------------------------------------------------------- */
+/* Host-buffer convenience entry (the end-to-end form: host fp32 gradient in,
+ * host fp32 decoded gradient out; H2D/D2H inside).  Encodes one user's chunk
+ * matrix with HSQ and decodes it again (ps_quantizer.py:36-43 for one user).
+ * Synchronous.  dev_scratch is a device buffer of gq_hsq_host_scratch_bytes(). */
+size_t gq_hsq_host_scratch_bytes(int64_t n_chunks, int d, int K, int n_seg);
+int gq_hsq_roundtrip_host(const float *host_grad, float *host_out, int64_t n_chunks, int d,
+                          const float *dev_codebook, int K, const int64_t *dev_seg_start, int n_seg,
+                          int n_bit, int random, uint64_t philox_seed, uint64_t philox_offset,
+                          void *dev_scratch, size_t scratch_bytes, int algo, gq_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GQB200_H */

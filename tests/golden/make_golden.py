@@ -268,7 +268,8 @@ if __name__ == "__main__":
     hsq_case("hsq_d8_k256_n6", (128, 64), 8, 8, 6, True, 18)
     hsq_case("hsq_d32_k256_n6", (128, 64), 32, 8, 6, True, 19)
     hsq_case("hsq_d16_k4096_n6", (128, 64), 16, 12, 6, True, 20)
-    hsq_case("hsq_d16to24_k256_n6", (64, 3, 3, 3), 16, 8, 6, True, 21)  # 1728 -> dim 24
+    hsq_case("hsq_conv1_d16_k256_n6", (64, 3, 3, 3), 16, 8, 6, True, 21)
+    hsq_case("hsq_d16to24_k256_n6", (45, 24), 16, 8, 6, True, 22)  # 1080 -> dim 24
     qsgd_case("qsgd_d128_n2", (64, 256), 128, 2, True, 31)
     qsgd_case("qsgd_d128to192_n2", (64, 3, 3, 3), 128, 2, True, 32)
     qsgd_case("terngrad_n1", (64, 64), 0, 1, True, 33)

@@ -1,0 +1,111 @@
+"""CPU: host-side logic -- dim rule, fvecs I/O, fused-plan layout, drop-in names."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+import gq_b200
+from gq_b200.compressors._common import chunk_dim, load_codebook
+from gq_b200.quantizers.fused import FusedPlan
+from gq_b200.utils import vecs_io
+from oracle import gq_oracle as O
+from util import FCN_SHAPES, codebook, make_args, resnet50_shapes
+
+
+def test_chunk_dim_rule():
+    assert chunk_dim(1728, 16) == 16          # first ResNet conv divides by 16
+    assert chunk_dim(1080, 16) == 24          # 16 -> 24
+    assert chunk_dim(1728, 128) == 192        # QSGD d=128 -> 192
+    assert chunk_dim(200704, 16) == 16
+    assert chunk_dim(10, 16) == 10            # smaller than c_dim -> whole tensor
+    assert chunk_dim(4096, 0) == 4096         # c_dim == 0 -> whole tensor (TernGrad)
+    for size in (1728, 2560, 200704, 1000, 37, 65536):
+        for c in (0, 8, 16, 32, 128):
+            assert chunk_dim(size, c) == O.chunk_dim(size, c)
+
+
+def test_codebook_rows_are_unit_norm_and_match_oracle():
+    for d, K in ((8, 256), (16, 256), (32, 256), (16, 4096)):
+        cb = load_codebook(d, K)
+        assert cb.shape == (K, d) and cb.dtype == np.float32
+        assert np.allclose(np.linalg.norm(cb.astype(np.float64), axis=1), 1.0, atol=1e-6)
+        assert np.array_equal(cb, codebook(d, K))
+
+
+def test_fvecs_roundtrip(tmp_path):
+    a = np.random.RandomState(0).standard_normal((7, 5)).astype(np.float32)
+    p = str(tmp_path / "x.fvecs")
+    vecs_io.fvecs_writer(p, a)
+    assert os.path.getsize(p) == 7 * 6 * 4
+    assert np.array_equal(vecs_io.fvecs_read(p), a)
+    assert np.array_equal(np.asarray(vecs_io.mmap_fvecs(p)), a)
+    q = str(tmp_path / "x.ivecs")
+    vecs_io.ivecs_writer(q, np.arange(12).reshape(3, 4))
+    assert np.array_equal(vecs_io.ivecs_read(q), np.arange(12).reshape(3, 4))
+
+
+def test_fused_plan_layout_resnet50_hsq():
+    plan = FusedPlan(gq_b200.NearestNeighborCompressor, resnet50_shapes(), make_args(), torch.device("cpu"), 2)
+    assert plan.total_elems() == 23520842
+    assert plan.compressed_elems() == 23498432
+    kinds = [g.kind for g in plan.groups]
+    assert kinds == ["hsq", "identity"]
+    g16, gid = plan.groups
+    assert g16.key == (16, 256)
+    assert g16.n_seg == 76 and g16.n_chunks == 23498432 // 16 == 1468652
+    assert gid.n == 22410
+    # every tensor has its own disjoint slot, groups are 256-byte aligned
+    spans = sorted((plan.tensor_off[i], plan.tensor_off[i] + plan.sizes[i]) for i in range(len(plan.sizes)))
+    for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+        assert a1 <= b0
+    for g in plan.groups:
+        assert (g.arena_off * 4) % 256 == 0
+    # wire format: 2 bytes per chunk + lb/ub + identity fp32
+    assert plan.wire_bytes() == 2 * g16.n_chunks + 8 * 76 + 4 * 22410
+    assert plan.record_bytes % 256 == 0 and plan.records.shape == (2, plan.record_bytes)
+    v = plan.view(0)
+    assert v.shape == (64, 3, 3, 3)
+
+
+def test_fused_plan_layout_other_codecs():
+    a = make_args(c_dim=128, n_bit=2)
+    plan = FusedPlan(gq_b200.QSGDCompressor, resnet50_shapes(), a, torch.device("cpu"), 1)
+    assert [g.key for g in plan.groups if g.kind == "qsgd"] == [192, 128]
+    tern = FusedPlan(gq_b200.QSGDCompressor, FCN_SHAPES, make_args(c_dim=0, n_bit=1), torch.device("cpu"), 1)
+    g = tern.groups[0]
+    assert g.key == "tensor" and g.n_chunks == 2 and g.bits == 4
+    topk = FusedPlan(gq_b200.TopKSparsificationCompressor, FCN_SHAPES, make_args(cr=100), torch.device("cpu"), 1)
+    assert topk.groups[0].k_total == 200704 // 100 + 2560 // 100
+    sign = FusedPlan(gq_b200.SignSGDCompressor, FCN_SHAPES, make_args(), torch.device("cpu"), 1)
+    assert sign.wire_bytes() == (203264 + 3) // 4 + 4 * 266
+
+
+def test_split_uniform_stream_follows_reference_call_order():
+    plan = FusedPlan(gq_b200.NearestNeighborCompressor, [(45, 24), (10,), (64, 64), (32, 64)],
+                     make_args(), torch.device("cpu"), 1)
+    n24, n16a, n16b = 1080 // 24, 4096 // 16, 2048 // 16
+    stream = np.arange(n24 + n16a + n16b, dtype=np.float32)
+    parts, used = plan.split_uniform_stream(stream)
+    assert used == stream.size
+    g24 = [g for g in plan.groups if g.kind == "hsq" and g.dim == 24][0]
+    g16 = [g for g in plan.groups if g.kind == "hsq" and g.dim == 16][0]
+    assert parts[id(g24)].tolist() == list(range(n24))
+    assert parts[id(g16)].tolist() == list(range(n24, n24 + n16a + n16b))
+
+
+def test_install_dropin_registers_reference_module_names():
+    saved = {k: sys.modules.get(k) for k in ("compressors", "quantizers", "utils", "utils.vecs_io", "utils.vec_np")}
+    try:
+        gq_b200.install_dropin()
+        import compressors
+        import quantizers
+        from utils.vecs_io import fvecs_read  # noqa: F401
+        assert compressors.NearestNeighborCompressor is gq_b200.NearestNeighborCompressor
+        assert quantizers.Quantizer is gq_b200.Quantizer
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
