@@ -52,6 +52,8 @@ _SIGNATURES = {
                                        c_void_p, c_void_p]),
     "gq_pvc_search": (c_int, [c_void_p, c_i64, c_int, c_void_p, c_int, c_void_p, c_u64, c_u64, c_void_p,
                               c_int, c_void_p, c_void_p]),
+    "gq_hsq_tc_debug": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                c_int, c_void_p]),
     "gq_axpy": (c_int, [c_void_p, c_void_p, c_float, c_i64, c_void_p, c_void_p]),
     "gq_sub": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_void_p]),
     "gq_hsq_host_scratch_bytes": (c_size, [c_i64, c_int, c_int, c_int]),
@@ -125,20 +127,16 @@ def f32c(t, what="tensor"):
 
 
 class PhiloxState:
-    """Seed/offset bookkeeping for the on-device Philox stream: the seed follows
-    torch.manual_seed, the offset advances by the number of uniforms each call
-    consumes, so runs are reproducible for a fixed call sequence."""
-
-    def __init__(self):
-        self._seed = None
-        self.offset = 0
+    """Seed/offset bookkeeping for the on-device Philox stream.  The state is torch's
+    own CUDA generator: the seed follows torch.manual_seed, the offset is read from and
+    advanced on torch.cuda.default_generators[device], so torch.manual_seed(s) replays
+    the same draws and interleaved torch.rand(device='cuda') calls never reuse them."""
 
     def take(self, n):
-        seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
-        if seed != self._seed:
-            self._seed, self.offset = seed, 0
-        off = self.offset
-        self.offset += (int(n) + 3) // 4 * 4
+        gen = torch.cuda.default_generators[torch.cuda.current_device()]
+        seed = gen.initial_seed() & 0xFFFFFFFFFFFFFFFF
+        off = int(gen.get_offset())
+        gen.set_offset(off + (int(n) + 3) // 4 * 4)
         return seed, off
 
 

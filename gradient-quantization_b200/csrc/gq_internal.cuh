@@ -34,4 +34,34 @@ int launch_f32_reduce_users(const float *in, int64_t user_stride, int n_users, i
 int launch_axpy(const float *a, const float *b, float alpha, int64_t n, float *out, int sub,
                 cudaStream_t st);
 
+// Per-chunk epilogue shared by all search kernels: store code and u, fold u into
+// the per-tensor min/max keys (lb/ub of the norm quantizer).
+template <typename CodeT>
+__device__ __forceinline__ void search_epilogue(bool valid, int64_t c, int best_k, float best_u,
+                                                CodeT *__restrict__ codes, float *__restrict__ u_out,
+                                                const int64_t *__restrict__ seg_start, int n_seg,
+                                                uint32_t *__restrict__ minmax_keys)
+{
+    if (valid) {
+        codes[c] = (CodeT)best_k;
+        u_out[c] = best_u;
+    }
+    if (minmax_keys == nullptr) return;
+    int seg = valid ? find_segment(seg_start, n_seg, c) : -1;
+    // warp-uniform fast path: every valid lane in the same tensor
+    int seg0 = __shfl_sync(0xffffffffu, seg, 0);
+    bool uniform = __all_sync(0xffffffffu, (seg == seg0) || !valid) && (seg0 >= 0);
+    if (uniform) {
+        float mn = warp_min(valid ? best_u : INFINITY);
+        float mx = warp_max(valid ? best_u : -INFINITY);
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(minmax_keys + 2 * seg0, float_to_key(mn));
+            atomicMax(minmax_keys + 2 * seg0 + 1, float_to_key(mx));
+        }
+    } else if (valid) {
+        atomicMin(minmax_keys + 2 * seg, float_to_key(best_u));
+        atomicMax(minmax_keys + 2 * seg + 1, float_to_key(best_u));
+    }
+}
+
 }  // namespace gq

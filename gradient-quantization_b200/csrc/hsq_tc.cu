@@ -1,15 +1,438 @@
-// hsq_tc.cu -- tcgen05 (TF32) nearest-codeword search with fp32 rescoring.
-// Placeholder until the tensor-core kernel lands: reports "unsupported" so that
-// GQ_ALGO_AUTO uses the exact CUDA-core kernel.
+// hsq_tc.cu -- tcgen05 (TF32) nearest-codeword search with exact fp32 rescoring,
+// for the headline shape d == 16, K == 256 (uint8 codes).
+//
+// Per 128-chunk tile the [128 x 16] x [16 x 256] inner-product contraction of
+// nearest_neighbor_compressor.py:68 runs on the 5th-gen tensor cores:
+//   TMA  : gradient tile (8 KB, row = chunk = 64 B, SWIZZLE_64B) -> smem ring;
+//          codebook (16 KB) -> smem once per CTA
+//   MMA  : 2 x tcgen05.mma kind::tf32 (M=128, N=256, K=8), fp32 accumulators in
+//          TMEM, two 256-column buffers so the next tile's MMA overlaps the epilogue
+//   EPI  : each of the 128 rows is one thread: tcgen05.ld its 256 approximate
+//          scores, keep only max|.| per group of 8 codewords (never touches HBM),
+//          then RESCORE in exact fp32 every codeword of every group whose maximum
+//          lies within 2*eps of the row maximum.
+// Bit-exactness argument: |approx_k - exact_k| <= eps(v) for all k  =>  the exact
+// argmax (and every exact tie) has approx >= max_approx - 2 eps, so it is inside
+// the rescored set; the rescoring is the same ascending-j FMA chain and the same
+// "first index wins" rule as hsq_exact.cu, hence identical codes and u.
+// eps(v) = 1.5 * 2^-9 * ||v||_2 covers TF32 operand truncation (2^-10 relative per
+// operand, unit-norm codewords, Cauchy-Schwarz) with a 1.5x safety factor; rows
+// with a non-finite norm rescore all 256 codewords.
+#include <cuda.h>
+
+#include <mutex>
+#include <vector>
+
 #include "gq_internal.cuh"
 
 namespace gq {
-bool hsq_tc_supported(int, int, int) { return false; }
-size_t hsq_tc_workspace_bytes(int64_t) { return 0; }
-int hsq_search_tc(const float *, int64_t, int, const float *, int, void *, int, float *, const int64_t *,
-                  int, uint32_t *, void *, size_t, cudaStream_t)
+namespace tc {
+
+constexpr int kD = 16;
+constexpr int kK = 256;
+constexpr int kTileM = 128;
+constexpr int kStages = 6;
+constexpr int kThreads = 384;  // 4 control warps + 2 x 4 epilogue warps
+constexpr uint32_t kTileBytes = kTileM * kD * 4;  // 8192
+constexpr uint32_t kCbBytes = kK * kD * 4;        // 16384
+constexpr int kGroup = 8;                         // codewords per rescoring group
+constexpr int kNumGroups = kK / kGroup;           // 32
+constexpr float kMargin = 3.0f / 512.0f;          // 2 * eps / ||v||
+
+constexpr uint32_t kOffA = 0;
+constexpr uint32_t kOffCb = kStages * kTileBytes;
+constexpr uint32_t kOffBar = kOffCb + kCbBytes;
+constexpr uint32_t kSmemBytes = kOffBar + 256 + 1024;  // + alignment slack
+
+// instruction descriptor: D fp32, A/B TF32, both K-major, N = 256, M = 128
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((kK >> 3) << 17) | ((kTileM >> 4) << 24);
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
-    set_error("tcgen05 search not built");
-    return GQ_ERR_UNSUPPORTED;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok;
+}
+// bounded wait: a protocol bug traps (sticky error, process exits) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, SWIZZLE_64B operand: rows of 64 B, 8-row groups 512 B apart
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;           // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(512 >> 4) << 32;  // stride byte offset
+    d |= (uint64_t)1 << 46;           // descriptor version (Blackwell)
+    d |= (uint64_t)4 << 61;           // SWIZZLE_64B
+    return d;
+}
+
+__device__ __forceinline__ void mma_tf32(uint32_t taddr, uint64_t adesc, uint64_t bdesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(taddr), "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float absmax3(float m, uint32_t a, uint32_t b)
+{
+    return fmaxf(m, fmaxf(fabsf(__uint_as_float(a)), fabsf(__uint_as_float(b))));
+}
+
+// exact fp32 score of codeword k against v (same chain as hsq_exact.cu); the codebook
+// sits in smem in the MMA's swizzled layout: 16-byte unit u of row k is at unit u ^ ((k >> 1) & 3)
+__device__ __forceinline__ float exact_score(const uint8_t *__restrict__ cb, int k, const float (&v)[kD])
+{
+    const uint8_t *row = cb + k * 64;
+    const int sw = (k >> 1) & 3;
+    const float4 c0 = *reinterpret_cast<const float4 *>(row + ((0 ^ sw) << 4));
+    const float4 c1 = *reinterpret_cast<const float4 *>(row + ((1 ^ sw) << 4));
+    const float4 c2 = *reinterpret_cast<const float4 *>(row + ((2 ^ sw) << 4));
+    const float4 c3 = *reinterpret_cast<const float4 *>(row + ((3 ^ sw) << 4));
+    float acc = __fmul_rn(c0.x, v[0]);
+    acc = __fmaf_rn(c0.y, v[1], acc);  acc = __fmaf_rn(c0.z, v[2], acc);  acc = __fmaf_rn(c0.w, v[3], acc);
+    acc = __fmaf_rn(c1.x, v[4], acc);  acc = __fmaf_rn(c1.y, v[5], acc);  acc = __fmaf_rn(c1.z, v[6], acc);
+    acc = __fmaf_rn(c1.w, v[7], acc);  acc = __fmaf_rn(c2.x, v[8], acc);  acc = __fmaf_rn(c2.y, v[9], acc);
+    acc = __fmaf_rn(c2.z, v[10], acc); acc = __fmaf_rn(c2.w, v[11], acc); acc = __fmaf_rn(c3.x, v[12], acc);
+    acc = __fmaf_rn(c3.y, v[13], acc); acc = __fmaf_rn(c3.z, v[14], acc); acc = __fmaf_rn(c3.w, v[15], acc);
+    return acc;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+hsq_search_tc_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_constant__ CUtensorMap map_cb,
+                     int64_t n_chunks, uint8_t *__restrict__ codes, float *__restrict__ u_out,
+                     const int64_t *__restrict__ seg_start, int n_seg, uint32_t *__restrict__ minmax_keys,
+                     float *__restrict__ dbg_scores, int dbg_tiles)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned, still a shared pointer
+    uint8_t *s_a = smem + kOffA;
+    uint8_t *s_cb = smem + kOffCb;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kOffBar);
+    // barrier slots: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], cb_full
+    const uint32_t bar_full = smem_u32(bars);
+    const uint32_t bar_empty = bar_full + 8 * kStages;
+    const uint32_t bar_tfull = bar_empty + 8 * kStages;
+    const uint32_t bar_tempty = bar_tfull + 16;
+    const uint32_t bar_cb = bar_tempty + 16;
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(smem + kOffBar + 8 * (2 * kStages + 5));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int64_t n_tiles = (n_chunks + kTileM - 1) / kTileM;
+    const int my_tiles = (blockIdx.x < n_tiles) ? (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 4);   // one arrive per epilogue warp of the tile
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bar_tfull + 8 * b, 1);
+            mbar_init(bar_tempty + 8 * b, 4);
+        }
+        mbar_init(bar_cb, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    if (warp == 0) {
+        // ------------------------------------------------------ TMA producer ---
+        if (lane == 0) {
+            mbar_expect_tx(bar_cb, kCbBytes);
+            tma_load_2d(smem_u32(s_cb), &map_cb, bar_cb, 0, 0);
+            for (int it = 0; it < my_tiles; ++it) {
+                const int s = it % kStages;
+                const int64_t tile = blockIdx.x + (int64_t)it * gridDim.x;
+                mbar_wait(bar_empty + 8 * s, ((it / kStages) & 1) ^ 1);
+                mbar_expect_tx(bar_full + 8 * s, kTileBytes);
+                tma_load_2d(smem_u32(s_a + s * kTileBytes), &map_grad, bar_full + 8 * s, 0, (int)(tile * kTileM));
+            }
+        }
+    } else if (warp == 1) {
+        // -------------------------------------------------------- MMA issuer ---
+        if (lane == 0) {
+            mbar_wait(bar_cb, 0);
+            const uint64_t bdesc = make_desc(smem_u32(s_cb));
+            for (int it = 0; it < my_tiles; ++it) {
+                const int s = it % kStages;
+                const int b = it & 1;
+                mbar_wait(bar_tempty + 8 * b, ((it >> 1) & 1) ^ 1);   // epilogue drained this TMEM buffer
+                mbar_wait(bar_full + 8 * s, (it / kStages) & 1);      // TMA landed this tile
+                tc_fence_after();
+                const uint64_t adesc = make_desc(smem_u32(s_a + s * kTileBytes));
+                const uint32_t taddr = tmem_base + (uint32_t)(b * kK);
+                mma_tf32(taddr, adesc, bdesc, 0u);              // k = 0..7   (bytes  0..31 of each row)
+                mma_tf32(taddr, adesc + 2, bdesc + 2, 1u);      // k = 8..15  (bytes 32..63): +32 B = +2 units
+                mma_commit(bar_tfull + 8 * b);
+            }
+        }
+    } else if (warp >= 4) {
+        // ----------------------------------------------------------- epilogue ---
+        const int egroup = (warp - 4) >> 2;   // 0: even local tiles (TMEM buffer 0), 1: odd
+        const int quad = warp & 3;            // TMEM lane quadrant this warp may read
+        const int row = quad * 32 + lane;     // row of the tile == TMEM lane
+        for (int it = egroup; it < my_tiles; it += 2) {
+            const int s = it % kStages;
+            const int b = it & 1;
+            const int64_t tile = blockIdx.x + (int64_t)it * gridDim.x;
+            const int64_t c = tile * kTileM + row;
+            const bool valid = c < n_chunks;
+            mbar_wait(bar_full + 8 * s, (it / kStages) & 1);   // TMA data visible to this thread
+            mbar_wait(bar_tfull + 8 * b, (it >> 1) & 1);       // accumulators complete
+            tc_fence_after();
+
+            // pass over the 256 approximate scores of this row: max |.| per group of 8
+            float gm[kNumGroups];
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * kK);
+#pragma unroll
+            for (int blk = 0; blk < kK / 32; ++blk) {
+                uint32_t sc[32];
+                tmem_ld32(taddr + blk * 32, sc);
+                tmem_ld_wait();
+                if (dbg_scores != nullptr && tile < dbg_tiles) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        dbg_scores[(tile * kTileM + row) * kK + blk * 32 + j] = __uint_as_float(sc[j]);
+                }
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    float m = fmaxf(fabsf(__uint_as_float(sc[8 * g])), fabsf(__uint_as_float(sc[8 * g + 1])));
+                    m = absmax3(m, sc[8 * g + 2], sc[8 * g + 3]);
+                    m = absmax3(m, sc[8 * g + 4], sc[8 * g + 5]);
+                    m = absmax3(m, sc[8 * g + 6], sc[8 * g + 7]);
+                    gm[blk * 4 + g] = m;
+                }
+            }
+            // TMEM buffer b may be overwritten by the MMA of local tile it + 2
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
+
+            // this row's chunk, from the (swizzled) smem tile
+            float v[kD];
+            {
+                const uint8_t *arow = s_a + s * kTileBytes + row * 64;
+                const int sw = (row >> 1) & 3;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float4 t = *reinterpret_cast<const float4 *>(arow + ((u ^ sw) << 4));
+                    v[4 * u] = t.x; v[4 * u + 1] = t.y; v[4 * u + 2] = t.z; v[4 * u + 3] = t.w;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_empty + 8 * s);   // smem stage free for the producer
+
+            float amax = gm[0];
+#pragma unroll
+            for (int g = 1; g < kNumGroups; ++g) amax = fmaxf(amax, gm[g]);
+            float n2 = 0.0f;
+#pragma unroll
+            for (int j = 0; j < kD; ++j) n2 = fmaf(v[j], v[j], n2);
+            const float thr = amax - kMargin * sqrtf(n2);
+            uint32_t mask = 0;
+#pragma unroll
+            for (int g = 0; g < kNumGroups; ++g) mask |= (gm[g] >= thr) ? (1u << g) : 0u;
+            // non-finite or overflowing norm, NaN scores, or an empty set: rescore everything
+            if (!(n2 < 3.0e38f) || !(amax < 3.0e38f) || mask == 0u) mask = 0xffffffffu;
+
+            int best_bits = -1, best_k = 0;
+            float best_u = 0.0f;
+            while (mask) {
+                const int g = __ffs(mask) - 1;
+                mask &= mask - 1;
+#pragma unroll 4
+                for (int i = 0; i < kGroup; ++i) {
+                    const int k = g * kGroup + i;
+                    const float p = exact_score(s_cb, k, v);
+                    const int ab = __float_as_int(p) & 0x7fffffff;
+                    if (ab > best_bits) { best_bits = ab; best_k = k; best_u = p; }
+                }
+            }
+            __syncwarp();
+            search_epilogue<uint8_t>(valid, c, best_k, best_u, codes, u_out, seg_start, n_seg, minmax_keys);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+// ------------------------------------------------------------------ host side ---
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+// rows x 16 fp32 matrix, box = 16 x box_rows, 64-byte swizzle, out-of-range rows read as zero
+static int make_map(CUtensorMap *map, const float *base, int64_t rows, int box_rows)
+{
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return GQ_ERR_CUDA;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)kD, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)kD * 4};
+    cuuint32_t box[2] = {(cuuint32_t)kD, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (base %p, rows %lld)", (int)r, (const void *)base,
+                  (long long)rows);
+        return GQ_ERR_CUDA;
+    }
+    return GQ_OK;
+}
+
+}  // namespace tc
+
+bool hsq_tc_supported(int d, int K, int code_bytes)
+{
+    if (d != tc::kD || K != tc::kK || code_bytes != 1) return false;
+    static int cc = -1;
+    if (cc < 0) {
+        int dev = 0, major = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) == cudaSuccess)
+            cc = major;
+        else
+            cc = 0;
+    }
+    return cc == 10 && tc::encode_fn() != nullptr;
+}
+
+size_t hsq_tc_workspace_bytes(int64_t) { return 0; }
+
+int hsq_search_tc_dbg(const float *grad, int64_t n_chunks, const float *codebook, void *codes, float *u_out,
+                      const int64_t *seg_start, int n_seg, uint32_t *minmax_keys, float *dbg_scores,
+                      int dbg_tiles, cudaStream_t st)
+{
+    GQ_REQUIRE(((uintptr_t)grad & 15) == 0 && ((uintptr_t)codebook & 15) == 0, "TMA needs 16-byte aligned bases");
+    GQ_REQUIRE(n_chunks < ((int64_t)1 << 31) - 256, "n_chunks too large for one tensor map");
+    CUtensorMap mg, mc;
+    int e = tc::make_map(&mg, grad, n_chunks, tc::kTileM);
+    if (e) return e;
+    e = tc::make_map(&mc, codebook, tc::kK, tc::kK);
+    if (e) return e;
+    static bool attr_set = false;
+    if (!attr_set) {
+        GQ_CUDA(cudaFuncSetAttribute(tc::hsq_search_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)tc::kSmemBytes));
+        attr_set = true;
+    }
+    const int64_t n_tiles = (n_chunks + tc::kTileM - 1) / tc::kTileM;
+    const int sms = sm_count();
+    const int grid = (int)(n_tiles < sms ? n_tiles : sms);
+    tc::hsq_search_tc_kernel<<<grid, tc::kThreads, tc::kSmemBytes, st>>>(
+        mg, mc, n_chunks, (uint8_t *)codes, u_out, seg_start, n_seg, minmax_keys, dbg_scores, dbg_tiles);
+    GQ_LAUNCH_CHECK("hsq_search_tc");
+    return GQ_OK;
+}
+
+int hsq_search_tc(const float *grad, int64_t n_chunks, int d, const float *codebook, int K, void *codes,
+                  int code_bytes, float *u_out, const int64_t *seg_start, int n_seg, uint32_t *minmax_keys,
+                  void *, size_t, cudaStream_t st)
+{
+    GQ_REQUIRE(hsq_tc_supported(d, K, code_bytes), "tcgen05 search: unsupported shape");
+    return hsq_search_tc_dbg(grad, n_chunks, codebook, codes, u_out, seg_start, n_seg, minmax_keys, nullptr, 0, st);
+}
+
 }  // namespace gq
+
+// Test hook: run the tcgen05 search and also dump the raw TF32 scores of the first
+// dbg_tiles tiles ([dbg_tiles*128, 256] fp32), so tests can measure the approximation
+// error the rescoring margin has to cover.
+extern "C" int gq_hsq_tc_debug(const float *grad, int64_t n_chunks, const float *codebook, void *codes,
+                               float *u_out, const int64_t *seg_start, int n_seg, float *dbg_scores,
+                               int dbg_tiles, gq_stream_t stream)
+{
+    using namespace gq;
+    GQ_REQUIRE(hsq_tc_supported(16, 256, 1), "tcgen05 search needs an sm_100 device");
+    return hsq_search_tc_dbg(grad, n_chunks, codebook, codes, u_out, seg_start, n_seg, nullptr, dbg_scores,
+                             dbg_tiles, as_stream(stream));
+}

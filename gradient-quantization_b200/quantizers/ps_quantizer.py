@@ -110,7 +110,12 @@ class PSQuantizer(QuantizerBase):
 
     def _apply_per_parameter(self):
         for i, param in enumerate(self.parameters):
-            g = torch.stack(self.compressed_gradients[i], dim=0).mean(dim=0)
+            # stack(...).mean(0) with the reference's CPU semantics: sum in user order,
+            # then a true division (torch's CUDA mean multiplies by 1/U instead)
+            stacked = torch.stack([_lib.f32c(t) for t in self.compressed_gradients[i]], dim=0)
+            g = torch.empty_like(stacked[0])
+            _lib.call("gq_f32_reduce_users", _lib.ptr(stacked), g.numel() * 4, stacked.shape[0],
+                      g.numel(), 1, 0, _lib.ptr(g), _lib.stream())
             if self.two_phase:
                 if self.error_feedback:
                     g.add_(param.server_error)

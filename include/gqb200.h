@@ -47,7 +47,7 @@ extern "C" {
 
 /* HSQ search algorithm selector */
 #define GQ_ALGO_AUTO 0   /* tcgen05 path when (d, K) allow it, else exact CUDA-core */
-#define GQ_ALGO_EXACT 1  /* fp32 CUDA-core search (any d <= 64, any K)              */
+#define GQ_ALGO_EXACT 1  /* fp32 CUDA-core search (any d <= 128, any K)             */
 #define GQ_ALGO_TC 2     /* tcgen05 TF32 search + fp32 rescoring (d == 16, K == 256) */
 
 typedef void *gq_stream_t; /* cudaStream_t */
@@ -204,6 +204,14 @@ int gq_topk_scatter_reduce(const int32_t *idx, const float *val, int64_t user_st
 int gq_pvc_search(const float *grad, int64_t n_chunks, int d, const float *dagger, int K,
                   const float *uniforms, uint64_t philox_seed, uint64_t philox_offset,
                   void *codes, int code_bytes, float *u_out, gq_stream_t stream);
+
+/* Diagnostic hook for the tcgen05 path (d == 16, K == 256): runs the search and
+ * also dumps the raw TF32 tensor-core scores of the first dbg_tiles 128-chunk
+ * tiles (fp32 [dbg_tiles*128, 256], device) so tests can measure the
+ * approximation error that the fp32 rescoring margin has to cover. */
+int gq_hsq_tc_debug(const float *grad, int64_t n_chunks, const float *codebook, void *codes,
+                    float *u_out, const int64_t *seg_start, int n_seg, float *dbg_scores,
+                    int dbg_tiles, gq_stream_t stream);
 
 /* ------------------------------------------------------------------------- */
 /* Elementwise helpers the quantizers need around the codecs.

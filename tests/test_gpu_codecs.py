@@ -39,7 +39,7 @@ def test_qsgd_golden(name):
 def test_qsgd_packed_wire_roundtrip(c_dim, n_bit):
     """packed record -> decode-reduce equals the unpacked reference-dtype path, per user and averaged."""
     from gq_b200.quantizers.fused import FusedPlan
-    shapes = [(64, 128), (100,), (32, 64), (40, 3, 3, 3)]
+    shapes = [(64, 128), (100,), (32, 64), (40, 3, 3, 4)]   # 1440 -> dim 288 (c_dim 128) / 96 (64)
     U = 3
     a = make_args(c_dim=c_dim, n_bit=n_bit, num_users=U)
     plan = FusedPlan(gq_b200.QSGDCompressor, shapes, a, torch.device(DEV), U)
