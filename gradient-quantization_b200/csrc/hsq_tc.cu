@@ -19,6 +19,7 @@
 // operand, unit-norm codewords, Cauchy-Schwarz) with a 1.5x safety factor; rows
 // with a non-finite norm rescore all 256 codewords.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include <mutex>
 #include <vector>
@@ -158,7 +159,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 hsq_search_tc_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_constant__ CUtensorMap map_cb,
                      int64_t n_chunks, uint8_t *__restrict__ codes, float *__restrict__ u_out,
                      const int64_t *__restrict__ seg_start, int n_seg, uint32_t *__restrict__ minmax_keys,
-                     float *__restrict__ dbg_scores, int dbg_tiles)
+                     float *__restrict__ dbg_scores, int dbg_tiles, int flags)
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned, still a shared pointer
@@ -244,6 +245,7 @@ hsq_search_tc_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_
             const bool valid = c < n_chunks;
             mbar_wait(bar_full + 8 * s, (it / kStages) & 1);   // TMA data visible to this thread
             mbar_wait(bar_tfull + 8 * b, (it >> 1) & 1);       // accumulators complete
+            __syncwarp();                                      // converged before .sync.aligned TMEM loads
             tc_fence_after();
 
             // pass over the 256 approximate scores of this row: max |.| per group of 8
@@ -284,19 +286,26 @@ hsq_search_tc_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_
                     v[4 * u] = t.x; v[4 * u + 1] = t.y; v[4 * u + 2] = t.z; v[4 * u + 3] = t.w;
                 }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_empty + 8 * s);   // smem stage free for the producer
+            float n2 = 0.0f;
+#pragma unroll
+            for (int j = 0; j < kD; ++j) n2 = fmaf(v[j], v[j], n2);
+            // Release the smem stage to the TMA producer only after EVERY lane's loads of v have
+            // returned: the ballot consumes n2 (hence all four LDS of each lane), and the arrive
+            // address depends on the ballot.  Measured on B200: without this dependency the
+            // mbarrier arrive can be performed before the warp's last LDS.128 has read the stage
+            // (a plain __syncwarp() is elided by the compiler), the producer's next TMA then
+            // overwrites the row under the read -- tests/tc_diag.py shows v[12..15] of tile it+6.
+            const uint32_t all_loaded = __ballot_sync(0xffffffffu, !(n2 < 0.0f));   // always all ones
+            if (lane == 0) mbar_arrive(bar_empty + 8 * s + ((all_loaded == 0u) ? 8u : 0u));
 
             float amax = gm[0];
 #pragma unroll
             for (int g = 1; g < kNumGroups; ++g) amax = fmaxf(amax, gm[g]);
-            float n2 = 0.0f;
-#pragma unroll
-            for (int j = 0; j < kD; ++j) n2 = fmaf(v[j], v[j], n2);
             const float thr = amax - kMargin * sqrtf(n2);
             uint32_t mask = 0;
 #pragma unroll
             for (int g = 0; g < kNumGroups; ++g) mask |= (gm[g] >= thr) ? (1u << g) : 0u;
+            const uint32_t mask0 = mask;
             // non-finite or overflowing norm, NaN scores, or an empty set: rescore everything
             if (!(n2 < 3.0e38f) || !(amax < 3.0e38f) || mask == 0u) mask = 0xffffffffu;
 
@@ -314,6 +323,25 @@ hsq_search_tc_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_
                 }
             }
             __syncwarp();
+            if (dbg_scores != nullptr && valid) {
+                float *aux = dbg_scores + (size_t)dbg_tiles * kTileM * kK + c * 24;
+                for (int j = 0; j < kD; ++j) aux[8 + j] = v[j];
+                aux[0] = v[0];
+                aux[1] = amax;
+                aux[2] = (float)it;
+                aux[3] = (float)blockIdx.x;
+                float vs = 0.f;
+                for (int j = 0; j < kD; ++j) vs += v[j];
+                aux[4] = vs;
+                float cs = 0.f;
+                {
+                    const uint8_t *rowp = s_cb + best_k * 64;
+                    for (int j = 0; j < 16; ++j) cs += *reinterpret_cast<const float *>(rowp + j * 4);
+                }
+                aux[5] = cs;                       // order-independent of the swizzle: sum over the row
+                aux[6] = __uint_as_float(mask0);
+                aux[7] = thr;
+            }
             search_epilogue<uint8_t>(valid, c, best_k, best_u, codes, u_out, seg_start, n_seg, minmax_keys);
         }
     }
@@ -406,10 +434,16 @@ int hsq_search_tc_dbg(const float *grad, int64_t n_chunks, const float *codebook
         attr_set = true;
     }
     const int64_t n_tiles = (n_chunks + tc::kTileM - 1) / tc::kTileM;
-    const int sms = sm_count();
+    int sms = sm_count();
+    if (const char *g = getenv("GQ_TC_GRID")) {   // debugging aid: force few CTAs -> many tiles per CTA
+        int v = atoi(g);
+        if (v > 0 && v < sms) sms = v;
+    }
     const int grid = (int)(n_tiles < sms ? n_tiles : sms);
+    int flags = 0;
+    if (const char *f = getenv("GQ_TC_FLAGS")) flags = atoi(f);
     tc::hsq_search_tc_kernel<<<grid, tc::kThreads, tc::kSmemBytes, st>>>(
-        mg, mc, n_chunks, (uint8_t *)codes, u_out, seg_start, n_seg, minmax_keys, dbg_scores, dbg_tiles);
+        mg, mc, n_chunks, (uint8_t *)codes, u_out, seg_start, n_seg, minmax_keys, dbg_scores, dbg_tiles, flags);
     GQ_LAUNCH_CHECK("hsq_search_tc");
     return GQ_OK;
 }
