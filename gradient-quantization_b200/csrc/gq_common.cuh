@@ -100,6 +100,24 @@ __device__ __forceinline__ int find_segment(const int64_t *__restrict__ seg_star
     return lo;
 }
 
+// Per-thread cache of the last segment looked up.  Grid-stride loops visit increasing
+// indices, so almost every lookup is two compares instead of a binary search of
+// dependent loads (tensors hold 64 .. 147 456 chunks).
+struct SegCache {
+    int seg = 0;
+    int64_t lo = 0, hi = 0;   // cached segment covers [lo, hi); empty at start
+};
+__device__ __forceinline__ int cached_segment(SegCache &sc, const int64_t *__restrict__ seg_start, int n_seg,
+                                              int64_t i)
+{
+    if (i < sc.lo || i >= sc.hi) {
+        sc.seg = find_segment(seg_start, n_seg, i);
+        sc.lo = __ldg(seg_start + sc.seg);
+        sc.hi = __ldg(seg_start + sc.seg + 1);
+    }
+    return sc.seg;
+}
+
 // ------------------------------------------------ reference scalar codecs ---
 // ProbabilisticScalarCompressor.compress, element-wise part
 // (compressors/probabilistic_scalar_compressor.py:17-26), exact op order.
@@ -116,9 +134,11 @@ __device__ __forceinline__ int psc_level(float v, float lb, float ub, float s, i
     return li;
 }
 // ProbabilisticScalarCompressor.decompress (probabilistic_scalar_compressor.py:31-32)
-__device__ __forceinline__ float psc_value(int l, float lb, float ub, float s)
+// s = 2^n is a power of two, so "/ s" is done as an exact multiplication by inv_s = 1/s
+// (identical result for every input, including subnormals).
+__device__ __forceinline__ float psc_value(int l, float lb, float ub, float inv_s)
 {
-    return __fadd_rn(__fdiv_rn(__fmul_rn((float)l, __fsub_rn(ub, lb)), s), lb);
+    return __fadd_rn(__fmul_rn(__fmul_rn((float)l, __fsub_rn(ub, lb)), inv_s), lb);
 }
 
 __device__ __forceinline__ float warp_min(float v)

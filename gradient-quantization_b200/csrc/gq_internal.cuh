@@ -40,14 +40,14 @@ template <typename CodeT>
 __device__ __forceinline__ void search_epilogue(bool valid, int64_t c, int best_k, float best_u,
                                                 CodeT *__restrict__ codes, float *__restrict__ u_out,
                                                 const int64_t *__restrict__ seg_start, int n_seg,
-                                                uint32_t *__restrict__ minmax_keys)
+                                                uint32_t *__restrict__ minmax_keys, SegCache &segc)
 {
     if (valid) {
         codes[c] = (CodeT)best_k;
         u_out[c] = best_u;
     }
     if (minmax_keys == nullptr) return;
-    int seg = valid ? find_segment(seg_start, n_seg, c) : -1;
+    int seg = valid ? cached_segment(segc, seg_start, n_seg, c) : -1;
     // warp-uniform fast path: every valid lane in the same tensor
     int seg0 = __shfl_sync(0xffffffffu, seg, 0);
     bool uniform = __all_sync(0xffffffffu, (seg == seg0) || !valid) && (seg0 >= 0);
@@ -61,6 +61,46 @@ __device__ __forceinline__ void search_epilogue(bool valid, int64_t c, int best_
     } else if (valid) {
         atomicMin(minmax_keys + 2 * seg, float_to_key(best_u));
         atomicMax(minmax_keys + 2 * seg + 1, float_to_key(best_u));
+    }
+}
+
+
+// Running per-tensor min/max of u kept in registers while a warp walks CONSECUTIVE chunks
+// (the tcgen05 kernel gives every CTA a contiguous range of tiles): one atomic pair per warp
+// per tensor instead of one per tile.  Both functions are warp-collective.
+struct MinMaxAcc {
+    int seg = -1;
+    float mn = INFINITY, mx = -INFINITY;
+};
+__device__ __forceinline__ void minmax_flush_warp(MinMaxAcc &a, uint32_t *__restrict__ keys)
+{
+    const uint32_t have = __ballot_sync(0xffffffffu, a.seg >= 0);
+    if (have != 0u) {
+        const int seg0 = __shfl_sync(0xffffffffu, a.seg, __ffs(have) - 1);
+        const bool uniform = __all_sync(0xffffffffu, a.seg == seg0 || a.seg < 0);
+        if (uniform) {
+            const float mn = warp_min(a.mn), mx = warp_max(a.mx);
+            if ((threadIdx.x & 31) == 0) {
+                atomicMin(keys + 2 * seg0, float_to_key(mn));
+                atomicMax(keys + 2 * seg0 + 1, float_to_key(mx));
+            }
+        } else if (a.seg >= 0) {
+            atomicMin(keys + 2 * a.seg, float_to_key(a.mn));
+            atomicMax(keys + 2 * a.seg + 1, float_to_key(a.mx));
+        }
+    }
+    a.seg = -1;
+    a.mn = INFINITY;
+    a.mx = -INFINITY;
+}
+__device__ __forceinline__ void minmax_add_warp(MinMaxAcc &a, bool valid, int seg, float u,
+                                                uint32_t *__restrict__ keys)
+{
+    if (__any_sync(0xffffffffu, valid && a.seg >= 0 && seg != a.seg)) minmax_flush_warp(a, keys);
+    if (valid) {
+        a.seg = seg;
+        a.mn = fminf(a.mn, u);
+        a.mx = fmaxf(a.mx, u);
     }
 }
 

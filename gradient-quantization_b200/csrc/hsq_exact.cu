@@ -34,6 +34,7 @@ hsq_search_exact_kernel(const float *__restrict__ grad, int64_t n_chunks,
         __syncthreads();
     }
 
+    SegCache segc;
     for (int64_t base = (int64_t)blockIdx.x * kSearchThreads; base < n_chunks;
          base += (int64_t)gridDim.x * kSearchThreads) {
         const int64_t c = base + tid;
@@ -108,7 +109,7 @@ hsq_search_exact_kernel(const float *__restrict__ grad, int64_t n_chunks,
                 if (ab > best_bits) { best_bits = ab; best_k = k0 + k; best_u = acc; }
             }
         }
-        search_epilogue<CodeT>(valid, c, best_k, best_u, codes, u_out, seg_start, n_seg, minmax_keys);
+        search_epilogue<CodeT>(valid, c, best_k, best_u, codes, u_out, seg_start, n_seg, minmax_keys, segc);
     }
 }
 
@@ -129,6 +130,7 @@ hsq_search_generic_kernel(const float *__restrict__ grad, int64_t n_chunks, int 
     float *s_cb = s_gen + 128 * pitch;   // [k_tile][d]
     const int tid = threadIdx.x;
 
+    SegCache segc;
     for (int64_t base = (int64_t)blockIdx.x * 128; base < n_chunks; base += (int64_t)gridDim.x * 128) {
         __syncthreads();
         // coalesced staging of 128 chunks
@@ -158,7 +160,7 @@ hsq_search_generic_kernel(const float *__restrict__ grad, int64_t n_chunks, int 
                 }
             }
         }
-        search_epilogue<CodeT>(valid, c, best_k, best_u, codes, u_out, seg_start, n_seg, minmax_keys);
+        search_epilogue<CodeT>(valid, c, best_k, best_u, codes, u_out, seg_start, n_seg, minmax_keys, segc);
     }
 }
 

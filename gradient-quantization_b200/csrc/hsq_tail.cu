@@ -16,11 +16,12 @@ __global__ void __launch_bounds__(256)
 seg_minmax_kernel(const float *__restrict__ u, int64_t n, const int64_t *__restrict__ seg_start,
                   int n_seg, uint32_t *__restrict__ keys)
 {
+    SegCache segc;
     for (int64_t base = (int64_t)blockIdx.x * 256; base < n; base += (int64_t)gridDim.x * 256) {
         int64_t i = base + threadIdx.x;
         bool valid = i < n;
         float x = valid ? u[i] : 0.0f;
-        int seg = valid ? find_segment(seg_start, n_seg, i) : -1;
+        int seg = valid ? cached_segment(segc, seg_start, n_seg, i) : -1;
         int seg0 = __shfl_sync(0xffffffffu, seg, 0);
         bool uniform = __all_sync(0xffffffffu, (seg == seg0) || !valid) && (seg0 >= 0);
         if (uniform) {
@@ -38,6 +39,8 @@ seg_minmax_kernel(const float *__restrict__ u, int64_t n, const int64_t *__restr
 }
 
 // ---------------------------------------------------------- norm quantize ---
+// Four consecutive chunks per thread: one float4 load of u (and of the uniforms), one
+// Philox4x32-10 block for the four draws, one packed store of the four levels.
 template <typename LT>
 __global__ void __launch_bounds__(256)
 norm_quantize_kernel(const float *__restrict__ u, int64_t n, const int64_t *__restrict__ seg_start,
@@ -49,15 +52,69 @@ norm_quantize_kernel(const float *__restrict__ u, int64_t n, const int64_t *__re
     if (blockIdx.x == 0) {
         for (int i = threadIdx.x; i < 2 * n_seg; i += 256) lbub[i] = key_to_float(keys[i]);
     }
-    for (int64_t base = (int64_t)blockIdx.x * 256; base < n; base += (int64_t)gridDim.x * 256) {
-        int64_t i = base + threadIdx.x;
-        if (i >= n) continue;
-        int seg = find_segment(seg_start, n_seg, i);
-        float lb = key_to_float(__ldg(keys + 2 * seg));
-        float ub = key_to_float(__ldg(keys + 2 * seg + 1));
-        float r = 0.0f;
-        if (random) r = uniforms ? __ldg(uniforms + i) : philox_uniform(seed, offset, (uint64_t)i);
-        l[i] = (LT)psc_level(u[i], lb, ub, s, random, r);
+    SegCache segc;
+    float lb = 0.0f, ub = 0.0f;
+    int cur = -1;
+    const int64_t n4 = (n + 3) / 4;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(u) & 15) == 0) &&
+                         (uniforms == nullptr || (reinterpret_cast<uintptr_t>(uniforms) & 15) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(l) & (4 * sizeof(LT) - 1)) == 0);
+    for (int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x; q < n4; q += (int64_t)gridDim.x * 256) {
+        const int64_t i0 = q * 4;
+        const bool full = aligned && (i0 + 3 < n);
+        float x[4], r[4] = {0.f, 0.f, 0.f, 0.f};
+        if (full) {
+            const float4 t = __ldg(reinterpret_cast<const float4 *>(u) + q);
+            x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w;
+        } else {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) x[t] = (i0 + t < n) ? u[i0 + t] : 0.0f;
+        }
+        if (random) {
+            if (uniforms) {
+                if (full) {
+                    const float4 t = __ldg(reinterpret_cast<const float4 *>(uniforms) + q);
+                    r[0] = t.x; r[1] = t.y; r[2] = t.z; r[3] = t.w;
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) r[t] = (i0 + t < n) ? uniforms[i0 + t] : 0.0f;
+                }
+            } else if (((offset + (uint64_t)i0) & 3u) == 0) {
+                const uint4 w = philox4x32_10(seed, (offset + (uint64_t)i0) >> 2);
+                r[0] = u01(w.x); r[1] = u01(w.y); r[2] = u01(w.z); r[3] = u01(w.w);
+            } else {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) r[t] = philox_uniform(seed, offset, (uint64_t)(i0 + t));
+            }
+        }
+        int lv[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int64_t i = i0 + t;
+            if (i < n) {
+                const int seg = cached_segment(segc, seg_start, n_seg, i);
+                if (seg != cur) {
+                    cur = seg;
+                    lb = key_to_float(__ldg(keys + 2 * seg));
+                    ub = key_to_float(__ldg(keys + 2 * seg + 1));
+                }
+                lv[t] = psc_level(x[t], lb, ub, s, random, r[t]);
+            } else {
+                lv[t] = 0;
+            }
+        }
+        if (full) {
+            if (sizeof(LT) == 1) {
+                reinterpret_cast<uint32_t *>(l)[q] =
+                    (uint32_t)lv[0] | ((uint32_t)lv[1] << 8) | ((uint32_t)lv[2] << 16) | ((uint32_t)lv[3] << 24);
+            } else {
+                reinterpret_cast<int4 *>(l)[q] = make_int4(lv[0], lv[1], lv[2], lv[3]);
+            }
+        } else {
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                if (i0 + t < n) l[i0 + t] = (LT)lv[t];
+        }
     }
 }
 
@@ -66,11 +123,12 @@ __global__ void __launch_bounds__(256)
 norm_dequantize_kernel(const LT *__restrict__ l, int64_t n, const int64_t *__restrict__ seg_start,
                        int n_seg, float s, const float *__restrict__ lbub, float *__restrict__ out)
 {
+    SegCache segc;
     for (int64_t base = (int64_t)blockIdx.x * 256; base < n; base += (int64_t)gridDim.x * 256) {
         int64_t i = base + threadIdx.x;
         if (i >= n) continue;
-        int seg = find_segment(seg_start, n_seg, i);
-        out[i] = psc_value((int)l[i], __ldg(lbub + 2 * seg), __ldg(lbub + 2 * seg + 1), s);
+        int seg = cached_segment(segc, seg_start, n_seg, i);
+        out[i] = psc_value((int)l[i], __ldg(lbub + 2 * seg), __ldg(lbub + 2 * seg + 1), 1.0f / s);
     }
 }
 
@@ -96,7 +154,7 @@ int launch_norm_quantize(const float *u, int64_t n, const int64_t *seg_start, in
                          int l_bytes, float *lbub, const uint32_t *keys, cudaStream_t st)
 {
     const float s = (float)(1u << n_bit);
-    const int grid = grid_for(n > 0 ? n : 1, 256);
+    const int grid = grid_for(n > 0 ? (n + 3) / 4 : 1, 256);
     if (l_bytes == 1)
         norm_quantize_kernel<uint8_t><<<grid, 256, 0, st>>>(u, n, seg_start, n_seg, s, random, uniforms,
                                                             seed, offset, (uint8_t *)l, lbub, keys);
@@ -122,17 +180,18 @@ int launch_norm_dequantize(const void *l, int l_bytes, int64_t n, const int64_t 
 }
 
 // ------------------------------------------------------- decode-and-reduce ---
-// One warp owns 32 consecutive chunks.  Phase A: lane <-> chunk, per user load
-// (code, l) and dequantize the norm once.  Phase B: lane <-> float4 of the
-// output row; (code, norm) of the owning chunk arrive by shuffle, the codeword
-// comes from shared memory (K*d*4 <= 64 KB) or L1/L2, products are added in
-// user order u = 0..U-1 with separately rounded mul and add, exactly like
-// torch.mul + stack().mean(0) of the reference.
-constexpr int kDecodeWarps = 8;
-constexpr int kMaxUsersUnrolled = 8;
+// One thread per float4 of the output, four independent float4 per thread (the loads of all
+// four are issued before any is consumed).  A chunk of D floats is D/4 consecutive float4, so
+// the D/4 lanes that share a chunk read the same code / level bytes (one coalesced request)
+// and dequantize the norm redundantly -- cheaper than a shuffle phase.  The codeword comes
+// from shared memory (K*d*4 <= 64 KB) or L1/L2; products are added in user order
+// u = 0..U-1 with separately rounded mul and add, exactly like torch.mul +
+// stack().mean(0) of the reference.
+constexpr int kDecodeThreads = 256;
+constexpr int kDecodeUnroll = 4;
 
 template <int D, typename CodeT, typename LT, bool CB_SMEM>
-__global__ void __launch_bounds__(kDecodeWarps * 32)
+__global__ void __launch_bounds__(kDecodeThreads)
 hsq_decode_reduce_kernel(const CodeT *__restrict__ codes, const LT *__restrict__ l,
                          const float *__restrict__ lbub, const float *__restrict__ norms_f32,
                          int64_t user_stride, int n_users, int64_t n_chunks,
@@ -141,82 +200,94 @@ hsq_decode_reduce_kernel(const CodeT *__restrict__ codes, const LT *__restrict__
                          int mean, int accumulate, float *__restrict__ out)
 {
     extern __shared__ float4 s_cbd[];
-    constexpr int D4 = D / 4;         // float4 per chunk
-    constexpr int ROWS = D4;          // warp rows (32 float4 each) per 32 chunks
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
+    constexpr int D4 = D / 4;  // float4 per chunk
     const float4 *cb4g = reinterpret_cast<const float4 *>(codebook);
     if (CB_SMEM) {
-        for (int i = threadIdx.x; i < K * D4; i += kDecodeWarps * 32) s_cbd[i] = __ldg(cb4g + i);
+        for (int i = threadIdx.x; i < K * D4; i += kDecodeThreads) s_cbd[i] = __ldg(cb4g + i);
         __syncthreads();
     }
-    const float inv_users = 1.0f;  // (division is done with __fdiv_rn below)
-    (void)inv_users;
-    const int64_t n_groups = (n_chunks + 31) / 32;
-    for (int64_t g = (int64_t)blockIdx.x * kDecodeWarps + warp; g < n_groups;
-         g += (int64_t)gridDim.x * kDecodeWarps) {
-        const int64_t c = g * 32 + lane;
-        const bool valid = c < n_chunks;
-        int seg = 0;
-        if (valid && n_bit != 32) seg = find_segment(seg_start, n_seg, c);
-        float4 acc[ROWS];
+    // mean = sum / U with the reference's true division; U == 1 and powers of two are exact
+    // as a multiplication by 1/U, everything else pays the IEEE division.
+    const float inv_s = 1.0f / s;
+    const float nu = (float)n_users;
+    const bool pow2 = (n_users & (n_users - 1)) == 0;
+    const float inv_nu = 1.0f / nu;
+    SegCache segc;
+    const int64_t n4 = n_chunks * D4;
+    constexpr int64_t kSpan = (int64_t)kDecodeThreads * kDecodeUnroll;
+    float4 *o4 = reinterpret_cast<float4 *>(out);
+    for (int64_t base = (int64_t)blockIdx.x * kSpan; base < n4; base += (int64_t)gridDim.x * kSpan) {
+        int64_t f[kDecodeUnroll], c[kDecodeUnroll];
+        int part[kDecodeUnroll], seg[kDecodeUnroll];
+        bool ok[kDecodeUnroll];
+        float4 acc[kDecodeUnroll];
 #pragma unroll
-        for (int i = 0; i < ROWS; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-
+        for (int j = 0; j < kDecodeUnroll; ++j) {
+            f[j] = base + j * kDecodeThreads + threadIdx.x;
+            ok[j] = f[j] < n4;
+            c[j] = ok[j] ? f[j] / D4 : 0;
+            part[j] = (int)(f[j] % D4);
+            seg[j] = (ok[j] && n_bit != 32) ? cached_segment(segc, seg_start, n_seg, c[j]) : 0;
+            acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         for (int u = 0; u < n_users; ++u) {
-            int code = 0;
-            float norm = 0.0f;
-            if (valid) {
-                const char *cu = reinterpret_cast<const char *>(codes) + u * user_stride;
-                code = (int)reinterpret_cast<const CodeT *>(cu)[c];
-                if (n_bit == 32) {
-                    const char *nu = reinterpret_cast<const char *>(norms_f32) + u * user_stride;
-                    norm = reinterpret_cast<const float *>(nu)[c];
-                } else {
-                    const char *lu = reinterpret_cast<const char *>(l) + u * user_stride;
-                    const char *bu = reinterpret_cast<const char *>(lbub) + u * user_stride;
-                    int lv = (int)reinterpret_cast<const LT *>(lu)[c];
-                    const float *b = reinterpret_cast<const float *>(bu);
-                    norm = psc_value(lv, __ldg(b + 2 * seg), __ldg(b + 2 * seg + 1), s);
+            const char *cu = reinterpret_cast<const char *>(codes) + u * user_stride;
+            int code[kDecodeUnroll];
+            float norm[kDecodeUnroll];
+            if (n_bit == 32) {
+                const char *nup = reinterpret_cast<const char *>(norms_f32) + u * user_stride;
+#pragma unroll
+                for (int j = 0; j < kDecodeUnroll; ++j) {
+                    code[j] = ok[j] ? (int)reinterpret_cast<const CodeT *>(cu)[c[j]] : 0;
+                    norm[j] = ok[j] ? reinterpret_cast<const float *>(nup)[c[j]] : 0.0f;
                 }
+            } else {
+                const char *lu = reinterpret_cast<const char *>(l) + u * user_stride;
+                const float *b = reinterpret_cast<const float *>(reinterpret_cast<const char *>(lbub) + u * user_stride);
+                int lv[kDecodeUnroll];
+#pragma unroll
+                for (int j = 0; j < kDecodeUnroll; ++j) {
+                    code[j] = ok[j] ? (int)reinterpret_cast<const CodeT *>(cu)[c[j]] : 0;
+                    lv[j] = ok[j] ? (int)reinterpret_cast<const LT *>(lu)[c[j]] : 0;
+                }
+#pragma unroll
+                for (int j = 0; j < kDecodeUnroll; ++j)
+                    norm[j] = psc_value(lv[j], __ldg(b + 2 * seg[j]), __ldg(b + 2 * seg[j] + 1), inv_s);
             }
 #pragma unroll
-            for (int i = 0; i < ROWS; ++i) {
-                const int f = i * 32 + lane;      // float4 index inside the 32-chunk group
-                const int slot = f / D4;          // owning chunk (lane of phase A)
-                const int part = f % D4;
-                const int cd = __shfl_sync(0xffffffffu, code, slot);
-                const float nm = __shfl_sync(0xffffffffu, norm, slot);
-                float4 cw = CB_SMEM ? s_cbd[cd * D4 + part] : __ldg(cb4g + (int64_t)cd * D4 + part);
+            for (int j = 0; j < kDecodeUnroll; ++j) {
+                const float4 cw = CB_SMEM ? s_cbd[code[j] * D4 + part[j]]
+                                          : __ldg(cb4g + (int64_t)code[j] * D4 + part[j]);
                 float4 pr;
-                pr.x = __fmul_rn(cw.x, nm); pr.y = __fmul_rn(cw.y, nm);
-                pr.z = __fmul_rn(cw.z, nm); pr.w = __fmul_rn(cw.w, nm);
+                pr.x = __fmul_rn(cw.x, norm[j]); pr.y = __fmul_rn(cw.y, norm[j]);
+                pr.z = __fmul_rn(cw.z, norm[j]); pr.w = __fmul_rn(cw.w, norm[j]);
                 if (u == 0) {
-                    acc[i] = pr;
+                    acc[j] = pr;
                 } else {
-                    acc[i].x = __fadd_rn(acc[i].x, pr.x); acc[i].y = __fadd_rn(acc[i].y, pr.y);
-                    acc[i].z = __fadd_rn(acc[i].z, pr.z); acc[i].w = __fadd_rn(acc[i].w, pr.w);
+                    acc[j].x = __fadd_rn(acc[j].x, pr.x); acc[j].y = __fadd_rn(acc[j].y, pr.y);
+                    acc[j].z = __fadd_rn(acc[j].z, pr.z); acc[j].w = __fadd_rn(acc[j].w, pr.w);
                 }
             }
         }
-        const float nu = (float)n_users;
-        float4 *o4 = reinterpret_cast<float4 *>(out) + g * 32 * D4;
 #pragma unroll
-        for (int i = 0; i < ROWS; ++i) {
-            const int f = i * 32 + lane;
-            const int64_t chunk = g * 32 + f / D4;
-            if (chunk >= n_chunks) continue;
-            float4 r = acc[i];
-            if (mean) {
-                r.x = __fdiv_rn(r.x, nu); r.y = __fdiv_rn(r.y, nu);
-                r.z = __fdiv_rn(r.z, nu); r.w = __fdiv_rn(r.w, nu);
+        for (int j = 0; j < kDecodeUnroll; ++j) {
+            if (!ok[j]) continue;
+            float4 r = acc[j];
+            if (mean && n_users > 1) {
+                if (pow2) {
+                    r.x = __fmul_rn(r.x, inv_nu); r.y = __fmul_rn(r.y, inv_nu);
+                    r.z = __fmul_rn(r.z, inv_nu); r.w = __fmul_rn(r.w, inv_nu);
+                } else {
+                    r.x = __fdiv_rn(r.x, nu); r.y = __fdiv_rn(r.y, nu);
+                    r.z = __fdiv_rn(r.z, nu); r.w = __fdiv_rn(r.w, nu);
+                }
             }
             if (accumulate) {
-                float4 o = o4[f];
+                const float4 o = o4[f[j]];
                 r.x = __fadd_rn(o.x, r.x); r.y = __fadd_rn(o.y, r.y);
                 r.z = __fadd_rn(o.z, r.z); r.w = __fadd_rn(o.w, r.w);
             }
-            o4[f] = r;
+            o4[f[j]] = r;
         }
     }
 }
@@ -249,7 +320,7 @@ hsq_decode_reduce_generic_kernel(const CodeT *__restrict__ codes, const LT *__re
                 const char *bu = reinterpret_cast<const char *>(lbub) + u * user_stride;
                 const float *b = reinterpret_cast<const float *>(bu);
                 norm = psc_value((int)reinterpret_cast<const LT *>(lu)[c], __ldg(b + 2 * seg),
-                                 __ldg(b + 2 * seg + 1), s);
+                                 __ldg(b + 2 * seg + 1), 1.0f / s);
             }
             float pr = __fmul_rn(__ldg(codebook + (int64_t)code * d + j), norm);
             acc = (u == 0) ? pr : __fadd_rn(acc, pr);
@@ -260,6 +331,153 @@ hsq_decode_reduce_generic_kernel(const CodeT *__restrict__ codes, const LT *__re
     }
 }
 
+// Power-of-two chunk sizes (D = 4, 8, 16), up to MAXU users: one warp owns 128 consecutive
+// chunks per iteration.  Lane L loads the code / level bytes of chunks L, L+32, L+64, L+96 for
+// every user up front (all requests in flight together, four coalesced 32-byte requests per
+// array and user), then walks the 4*D4 rows of 32 float4: the chunk of row r, lane L is
+// q = (32 r + L) / D4, its owner lane is q % 32 and its slot q / 32 = r / D4 is the same for
+// the whole warp, so (code, norm) arrive with two shuffles from statically indexed registers.
+// Rows are finished one at a time (4 accumulator registers), users innermost in user order.
+template <int D, int MAXU, typename CodeT, typename LT>
+__global__ void __launch_bounds__(kDecodeThreads)
+hsq_decode_reduce_warp_kernel(const CodeT *__restrict__ codes, const LT *__restrict__ l,
+                              const float *__restrict__ lbub, const float *__restrict__ norms_f32,
+                              int64_t user_stride, int n_users, int64_t n_chunks,
+                              const float *__restrict__ codebook, int K,
+                              const int64_t *__restrict__ seg_start, int n_seg, float s, int n_bit,
+                              int mean, int accumulate, float *__restrict__ out)
+{
+    extern __shared__ float4 s_cbd[];
+    constexpr int D4 = D / 4;
+    static_assert((D4 & (D4 - 1)) == 0 && D4 <= 4, "D = 4, 8 or 16");
+    const float4 *cb4g = reinterpret_cast<const float4 *>(codebook);
+    for (int i = threadIdx.x; i < K * D4; i += kDecodeThreads) s_cbd[i] = __ldg(cb4g + i);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    constexpr int kWarps = kDecodeThreads / 32;
+    const float inv_s = 1.0f / s;
+    const float nu = (float)n_users;
+    const bool pow2 = (n_users & (n_users - 1)) == 0;
+    const float inv_nu = 1.0f / nu;
+    SegCache segc;
+    const int64_t n_iter = (n_chunks + 127) / 128;
+    const int64_t n4 = n_chunks * D4;
+    float4 *o4 = reinterpret_cast<float4 *>(out);
+    for (int64_t itx = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5); itx < n_iter;
+         itx += (int64_t)gridDim.x * kWarps) {
+        const int64_t c0 = itx * 128;
+        int code[MAXU][4];
+        float nrm[MAXU][4];   // raw level (as float) or fp32 norm; dequantized below
+#pragma unroll
+        for (int u = 0; u < MAXU; ++u) {
+            if (u < n_users) {
+                const CodeT *cu = reinterpret_cast<const CodeT *>(reinterpret_cast<const char *>(codes) + u * user_stride);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int64_t c = c0 + t * 32 + lane;
+                    code[u][t] = (c < n_chunks) ? (int)cu[c] : 0;
+                }
+                if (n_bit == 32) {
+                    const float *nf = reinterpret_cast<const float *>(reinterpret_cast<const char *>(norms_f32) + u * user_stride);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const int64_t c = c0 + t * 32 + lane;
+                        nrm[u][t] = (c < n_chunks) ? nf[c] : 0.0f;
+                    }
+                } else {
+                    const LT *lu = reinterpret_cast<const LT *>(reinterpret_cast<const char *>(l) + u * user_stride);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const int64_t c = c0 + t * 32 + lane;
+                        nrm[u][t] = (c < n_chunks) ? (float)(int)lu[c] : 0.0f;
+                    }
+                }
+            }
+        }
+        if (n_bit != 32) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int64_t c = c0 + t * 32 + lane;
+                const int seg = (c < n_chunks) ? cached_segment(segc, seg_start, n_seg, c) : 0;
+#pragma unroll
+                for (int u = 0; u < MAXU; ++u) {
+                    if (u < n_users) {
+                        const float *b = reinterpret_cast<const float *>(reinterpret_cast<const char *>(lbub) + u * user_stride);
+                        const float lb = __ldg(b + 2 * seg), ub = __ldg(b + 2 * seg + 1);
+                        // l * (ub - lb) / 2^n + lb   (probabilistic_scalar_compressor.py:31-32)
+                        nrm[u][t] = __fadd_rn(__fmul_rn(__fmul_rn(nrm[u][t], __fsub_rn(ub, lb)), inv_s), lb);
+                    }
+                }
+            }
+        }
+        const int64_t f0 = c0 * D4;
+#pragma unroll
+        for (int r = 0; r < 4 * D4; ++r) {
+            const int fl = r * 32 + lane;
+            const int owner = (fl / D4) & 31;
+            const int part = fl % D4;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < MAXU; ++u) {
+                if (u < n_users) {
+                    const int cd = __shfl_sync(0xffffffffu, code[u][r / D4], owner);
+                    const float nm = __shfl_sync(0xffffffffu, nrm[u][r / D4], owner);
+                    const float4 cw = s_cbd[cd * D4 + part];
+                    float4 pr;
+                    pr.x = __fmul_rn(cw.x, nm); pr.y = __fmul_rn(cw.y, nm);
+                    pr.z = __fmul_rn(cw.z, nm); pr.w = __fmul_rn(cw.w, nm);
+                    if (u == 0) {
+                        acc = pr;
+                    } else {
+                        acc.x = __fadd_rn(acc.x, pr.x); acc.y = __fadd_rn(acc.y, pr.y);
+                        acc.z = __fadd_rn(acc.z, pr.z); acc.w = __fadd_rn(acc.w, pr.w);
+                    }
+                }
+            }
+            const int64_t f = f0 + fl;
+            if (f < n4) {
+                if (mean && n_users > 1) {
+                    if (pow2) {
+                        acc.x = __fmul_rn(acc.x, inv_nu); acc.y = __fmul_rn(acc.y, inv_nu);
+                        acc.z = __fmul_rn(acc.z, inv_nu); acc.w = __fmul_rn(acc.w, inv_nu);
+                    } else {
+                        acc.x = __fdiv_rn(acc.x, nu); acc.y = __fdiv_rn(acc.y, nu);
+                        acc.z = __fdiv_rn(acc.z, nu); acc.w = __fdiv_rn(acc.w, nu);
+                    }
+                }
+                if (accumulate) {
+                    const float4 o = o4[f];
+                    acc.x = __fadd_rn(o.x, acc.x); acc.y = __fadd_rn(o.y, acc.y);
+                    acc.z = __fadd_rn(o.z, acc.z); acc.w = __fadd_rn(o.w, acc.w);
+                }
+                o4[f] = acc;
+            }
+        }
+    }
+}
+
+template <int D, int MAXU, typename CodeT, typename LT>
+static int launch_decode_warp(const void *codes, const void *l, const float *lbub, const float *norms_f32,
+                              int64_t user_stride, int n_users, int64_t n_chunks, const float *codebook,
+                              int K, const int64_t *seg_start, int n_seg, float s, int n_bit, int mean,
+                              int accumulate, float *out, cudaStream_t st)
+{
+    const size_t cb_bytes = (size_t)K * D * 4;
+    auto kern = hsq_decode_reduce_warp_kernel<D, MAXU, CodeT, LT>;
+    GQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cb_bytes));
+    int occ = 1;
+    GQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kDecodeThreads, cb_bytes));
+    const int64_t iters = (n_chunks + 127) / 128;
+    const int64_t wblocks = (iters + kDecodeThreads / 32 - 1) / (kDecodeThreads / 32);
+    int64_t cap = (int64_t)sm_count() * (occ < 1 ? 1 : occ);
+    int grid = (int)(wblocks < cap ? wblocks : cap);
+    kern<<<grid < 1 ? 1 : grid, kDecodeThreads, cb_bytes, st>>>(
+        (const CodeT *)codes, (const LT *)l, lbub, norms_f32, user_stride, n_users, n_chunks, codebook, K,
+        seg_start, n_seg, s, n_bit, mean, accumulate, out);
+    GQ_LAUNCH_CHECK("hsq_decode_reduce_warp");
+    return GQ_OK;
+}
+
 template <int D, typename CodeT, typename LT>
 static int launch_decode_d(const void *codes, const void *l, const float *lbub, const float *norms_f32,
                            int64_t user_stride, int n_users, int64_t n_chunks, const float *codebook,
@@ -268,22 +486,34 @@ static int launch_decode_d(const void *codes, const void *l, const float *lbub, 
 {
     const float s = (n_bit == 32) ? 1.0f : (float)(1u << n_bit);
     const size_t cb_bytes = (size_t)K * D * 4;
-    const int64_t n_groups = (n_chunks + 31) / 32;
-    int64_t blocks = (n_groups + kDecodeWarps - 1) / kDecodeWarps;
-    if (cb_bytes <= 64 * 1024) {
+    const int64_t span = (int64_t)kDecodeThreads * kDecodeUnroll;
+    const int64_t blocks = (n_chunks * (D / 4) + span - 1) / span;
+    constexpr int D4c = D / 4;
+    constexpr bool kWarpPath = ((D4c & (D4c - 1)) == 0) && D4c <= 4;   // D = 4, 8, 16
+    constexpr int DW = kWarpPath ? D : 16;
+    if (kWarpPath && cb_bytes <= 64 * 1024 && n_users <= 8) {
+#define GQ_W(MU) return launch_decode_warp<DW, MU, CodeT, LT>(codes, l, lbub, norms_f32, user_stride, n_users, n_chunks, codebook, K, seg_start, n_seg, s, n_bit, mean, accumulate, out, st)
+        if (n_users == 1) GQ_W(1);
+        if (n_users == 2) GQ_W(2);
+        if (n_users <= 4) GQ_W(4);
+        GQ_W(8);
+#undef GQ_W
+    } else if (cb_bytes <= 64 * 1024) {
         auto kern = hsq_decode_reduce_kernel<D, CodeT, LT, true>;
         GQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cb_bytes));
-        // persistent: the codebook is staged once per CTA
-        int64_t cap = (int64_t)sm_count() * (cb_bytes <= 16 * 1024 ? 8 : 3);
+        // persistent: the codebook is staged once per CTA; exactly one resident wave
+        int occ = 1;
+        GQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kDecodeThreads, cb_bytes));
+        int64_t cap = (int64_t)sm_count() * (occ < 1 ? 1 : occ);
         int grid = (int)(blocks < cap ? blocks : cap);
-        kern<<<grid < 1 ? 1 : grid, kDecodeWarps * 32, cb_bytes, st>>>(
+        kern<<<grid < 1 ? 1 : grid, kDecodeThreads, cb_bytes, st>>>(
             (const CodeT *)codes, (const LT *)l, lbub, norms_f32, user_stride, n_users, n_chunks,
             codebook, K, seg_start, n_seg, s, n_bit, mean, accumulate, out);
     } else {
         auto kern = hsq_decode_reduce_kernel<D, CodeT, LT, false>;
         int64_t cap = (int64_t)sm_count() * 8;
         int grid = (int)(blocks < cap ? blocks : cap);
-        kern<<<grid < 1 ? 1 : grid, kDecodeWarps * 32, 0, st>>>(
+        kern<<<grid < 1 ? 1 : grid, kDecodeThreads, 0, st>>>(
             (const CodeT *)codes, (const LT *)l, lbub, norms_f32, user_stride, n_users, n_chunks,
             codebook, K, seg_start, n_seg, s, n_bit, mean, accumulate, out);
     }

@@ -32,17 +32,20 @@ namespace tc {
 constexpr int kD = 16;
 constexpr int kK = 256;
 constexpr int kTileM = 128;
-constexpr int kStages = 6;
+constexpr int kStages = 4;
 constexpr int kThreads = 384;  // 4 control warps + 2 x 4 epilogue warps
 constexpr uint32_t kTileBytes = kTileM * kD * 4;  // 8192
 constexpr uint32_t kCbBytes = kK * kD * 4;        // 16384
-constexpr int kGroup = 8;                         // codewords per rescoring group
-constexpr int kNumGroups = kK / kGroup;           // 32
+constexpr int kGroup = 4;                         // codewords per rescoring group
+constexpr int kNumGroups = kK / kGroup;           // 64
+constexpr uint32_t kPlaneBytes = kK * 128;        // one rescoring plane: 128-byte slot per codeword
+constexpr int kPlanes = 4;
 constexpr float kMargin = 3.0f / 512.0f;          // 2 * eps / ||v||
 
 constexpr uint32_t kOffA = 0;
 constexpr uint32_t kOffCb = kStages * kTileBytes;
-constexpr uint32_t kOffBar = kOffCb + kCbBytes;
+constexpr uint32_t kOffPlanes = kOffCb + kCbBytes;
+constexpr uint32_t kOffBar = kOffPlanes + kPlanes * kPlaneBytes;
 constexpr uint32_t kSmemBytes = kOffBar + 256 + 1024;  // + alignment slack
 
 // instruction descriptor: D fp32, A/B TF32, both K-major, N = 256, M = 128
@@ -75,10 +78,10 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
 // bounded wait: a protocol bug traps (sticky error, process exits) instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
+    // each try_wait suspends the thread for a hardware time slice before it reports failure
+    uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) __trap();
+        if (++spins > (1u << 24)) __trap();
     }
 }
 
@@ -136,16 +139,21 @@ __device__ __forceinline__ float absmax3(float m, uint32_t a, uint32_t b)
     return fmaxf(m, fmaxf(fabsf(__uint_as_float(a)), fabsf(__uint_as_float(b))));
 }
 
-// exact fp32 score of codeword k against v (same chain as hsq_exact.cu); the codebook
-// sits in smem in the MMA's swizzled layout: 16-byte unit u of row k is at unit u ^ ((k >> 1) & 3)
-__device__ __forceinline__ float exact_score(const uint8_t *__restrict__ cb, int k, const float (&v)[kD])
+// Exact fp32 score of codeword k against v (same chain as hsq_exact.cu).
+// Rescoring reads are lane-divergent (every lane wants a different codeword), so the
+// codebook is replicated in shared memory in 4 "planes" laid out such that the 8 lanes of
+// a quarter-warp always hit 8 different 16-byte bank groups, whatever codewords they ask for:
+// lane class c = lane & 7, rotation r = c >> 1, half h = c & 1; plane r stores codeword k in a
+// 128-byte slot, twice (h = 0, 1), with 16-byte unit u at bank group 4h + ((u + r) & 3).
+// cw_base = plane r + 64 h (per lane), uo[u] = 16 * ((u + r) & 3).
+__device__ __forceinline__ float exact_score(const uint8_t *__restrict__ cw_base, const uint32_t (&uo)[4], int k,
+                                             const float (&v)[kD])
 {
-    const uint8_t *row = cb + k * 64;
-    const int sw = (k >> 1) & 3;
-    const float4 c0 = *reinterpret_cast<const float4 *>(row + ((0 ^ sw) << 4));
-    const float4 c1 = *reinterpret_cast<const float4 *>(row + ((1 ^ sw) << 4));
-    const float4 c2 = *reinterpret_cast<const float4 *>(row + ((2 ^ sw) << 4));
-    const float4 c3 = *reinterpret_cast<const float4 *>(row + ((3 ^ sw) << 4));
+    const uint8_t *row = cw_base + k * 128;
+    const float4 c0 = *reinterpret_cast<const float4 *>(row + uo[0]);
+    const float4 c1 = *reinterpret_cast<const float4 *>(row + uo[1]);
+    const float4 c2 = *reinterpret_cast<const float4 *>(row + uo[2]);
+    const float4 c3 = *reinterpret_cast<const float4 *>(row + uo[3]);
     float acc = __fmul_rn(c0.x, v[0]);
     acc = __fmaf_rn(c0.y, v[1], acc);  acc = __fmaf_rn(c0.z, v[2], acc);  acc = __fmaf_rn(c0.w, v[3], acc);
     acc = __fmaf_rn(c1.x, v[4], acc);  acc = __fmaf_rn(c1.y, v[5], acc);  acc = __fmaf_rn(c1.z, v[6], acc);
@@ -157,7 +165,8 @@ __device__ __forceinline__ float exact_score(const uint8_t *__restrict__ cb, int
 
 __global__ void __launch_bounds__(kThreads, 1)
 hsq_search_tc_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_constant__ CUtensorMap map_cb,
-                     int64_t n_chunks, uint8_t *__restrict__ codes, float *__restrict__ u_out,
+                     const float *__restrict__ codebook, int64_t n_chunks, uint8_t *__restrict__ codes,
+                     float *__restrict__ u_out,
                      const int64_t *__restrict__ seg_start, int n_seg, uint32_t *__restrict__ minmax_keys,
                      float *__restrict__ dbg_scores, int dbg_tiles, int flags)
 {
@@ -165,6 +174,7 @@ hsq_search_tc_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned, still a shared pointer
     uint8_t *s_a = smem + kOffA;
     uint8_t *s_cb = smem + kOffCb;
+    uint8_t *s_planes = smem + kOffPlanes;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kOffBar);
     // barrier slots: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], cb_full
     const uint32_t bar_full = smem_u32(bars);
@@ -176,8 +186,11 @@ hsq_search_tc_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    // every CTA owns a contiguous range of tiles (balanced to within one tile)
     const int64_t n_tiles = (n_chunks + kTileM - 1) / kTileM;
-    const int my_tiles = (blockIdx.x < n_tiles) ? (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+    const int64_t tq = n_tiles / gridDim.x, trem = n_tiles % gridDim.x;
+    const int64_t tile0 = (int64_t)blockIdx.x * tq + min((int64_t)blockIdx.x, trem);
+    const int my_tiles = (int)(tq + (((int64_t)blockIdx.x < trem) ? 1 : 0));
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -191,6 +204,12 @@ hsq_search_tc_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_
         mbar_init(bar_cb, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    // rescoring planes (see exact_score): 4 planes x 256 codewords x 2 halves x 4 units
+    for (int i = threadIdx.x; i < kPlanes * kK * 8; i += kThreads) {
+        const int u = i & 3, h = (i >> 2) & 1, k = (i >> 3) & (kK - 1), r = i >> 11;
+        const float4 val = __ldg(reinterpret_cast<const float4 *>(codebook) + k * 4 + u);
+        *reinterpret_cast<float4 *>(s_planes + r * kPlaneBytes + k * 128 + 16 * (4 * h + ((u + r) & 3))) = val;
     }
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512));
@@ -208,7 +227,7 @@ hsq_search_tc_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_
             tma_load_2d(smem_u32(s_cb), &map_cb, bar_cb, 0, 0);
             for (int it = 0; it < my_tiles; ++it) {
                 const int s = it % kStages;
-                const int64_t tile = blockIdx.x + (int64_t)it * gridDim.x;
+                const int64_t tile = tile0 + it;
                 mbar_wait(bar_empty + 8 * s, ((it / kStages) & 1) ^ 1);
                 mbar_expect_tx(bar_full + 8 * s, kTileBytes);
                 tma_load_2d(smem_u32(s_a + s * kTileBytes), &map_grad, bar_full + 8 * s, 0, (int)(tile * kTileM));
@@ -237,10 +256,17 @@ hsq_search_tc_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_
         const int egroup = (warp - 4) >> 2;   // 0: even local tiles (TMEM buffer 0), 1: odd
         const int quad = warp & 3;            // TMEM lane quadrant this warp may read
         const int row = quad * 32 + lane;     // row of the tile == TMEM lane
+        const int rot = (lane & 7) >> 1, hlf = lane & 1;
+        const uint8_t *cw_base = s_planes + rot * kPlaneBytes + 64 * hlf;
+        uint32_t uo[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) uo[u] = 16u * ((u + rot) & 3);
+        SegCache segc;
+        MinMaxAcc mm;
         for (int it = egroup; it < my_tiles; it += 2) {
             const int s = it % kStages;
             const int b = it & 1;
-            const int64_t tile = blockIdx.x + (int64_t)it * gridDim.x;
+            const int64_t tile = tile0 + it;
             const int64_t c = tile * kTileM + row;
             const bool valid = c < n_chunks;
             mbar_wait(bar_full + 8 * s, (it / kStages) & 1);   // TMA data visible to this thread
@@ -248,7 +274,7 @@ hsq_search_tc_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_
             __syncwarp();                                      // converged before .sync.aligned TMEM loads
             tc_fence_after();
 
-            // pass over the 256 approximate scores of this row: max |.| per group of 8
+            // pass over the 256 approximate scores of this row: max |.| per group of 4 codewords
             float gm[kNumGroups];
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * kK);
 #pragma unroll
@@ -262,12 +288,9 @@ hsq_search_tc_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_
                         dbg_scores[(tile * kTileM + row) * kK + blk * 32 + j] = __uint_as_float(sc[j]);
                 }
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    float m = fmaxf(fabsf(__uint_as_float(sc[8 * g])), fabsf(__uint_as_float(sc[8 * g + 1])));
-                    m = absmax3(m, sc[8 * g + 2], sc[8 * g + 3]);
-                    m = absmax3(m, sc[8 * g + 4], sc[8 * g + 5]);
-                    m = absmax3(m, sc[8 * g + 6], sc[8 * g + 7]);
-                    gm[blk * 4 + g] = m;
+                for (int g = 0; g < 8; ++g) {
+                    float m = fmaxf(fabsf(__uint_as_float(sc[4 * g])), fabsf(__uint_as_float(sc[4 * g + 1])));
+                    gm[blk * 8 + g] = absmax3(m, sc[4 * g + 2], sc[4 * g + 3]);
                 }
             }
             // TMEM buffer b may be overwritten by the MMA of local tile it + 2
@@ -298,26 +321,34 @@ hsq_search_tc_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_
             const uint32_t all_loaded = __ballot_sync(0xffffffffu, !(n2 < 0.0f));   // always all ones
             if (lane == 0) mbar_arrive(bar_empty + 8 * s + ((all_loaded == 0u) ? 8u : 0u));
 
-            float amax = gm[0];
+            float amax = fmaxf(gm[0], gm[1]);
 #pragma unroll
-            for (int g = 1; g < kNumGroups; ++g) amax = fmaxf(amax, gm[g]);
+            for (int g = 2; g < kNumGroups; g += 2) amax = fmaxf(amax, fmaxf(gm[g], gm[g + 1]));
             const float thr = amax - kMargin * sqrtf(n2);
-            uint32_t mask = 0;
+            // candidate groups: gm[g] >= thr.  d = gm - thr on the FMA pipe, sign bits funnelled
+            // into two 32-bit words (bit g of below[g >> 5] set = group g is below the threshold).
+            uint32_t bl[4] = {0u, 0u, 0u, 0u};   // four independent chains of 16 groups each
 #pragma unroll
-            for (int g = 0; g < kNumGroups; ++g) mask |= (gm[g] >= thr) ? (1u << g) : 0u;
-            const uint32_t mask0 = mask;
+            for (int g = 15; g >= 0; --g) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    bl[q] = __funnelshift_l(__float_as_uint(gm[16 * q + g] - thr), bl[q], 1);
+            }
+            uint64_t cand = ~(((uint64_t)(bl[0] & 0xffffu)) | ((uint64_t)(bl[1] & 0xffffu) << 16) |
+                              ((uint64_t)(bl[2] & 0xffffu) << 32) | ((uint64_t)(bl[3] & 0xffffu) << 48));
             // non-finite or overflowing norm, NaN scores, or an empty set: rescore everything
-            if (!(n2 < 3.0e38f) || !(amax < 3.0e38f) || mask == 0u) mask = 0xffffffffu;
+            if (!(n2 < 3.0e38f) || !(amax < 3.0e38f) || cand == 0ull) cand = ~0ull;
+            const uint32_t mask0 = (uint32_t)cand;
 
             int best_bits = -1, best_k = 0;
             float best_u = 0.0f;
-            while (mask) {
-                const int g = __ffs(mask) - 1;
-                mask &= mask - 1;
-#pragma unroll 4
+            while (cand) {
+                const int g = __ffsll((long long)cand) - 1;
+                cand &= cand - 1;
+#pragma unroll
                 for (int i = 0; i < kGroup; ++i) {
                     const int k = g * kGroup + i;
-                    const float p = exact_score(s_cb, k, v);
+                    const float p = exact_score(cw_base, uo, k, v);
                     const int ab = __float_as_int(p) & 0x7fffffff;
                     if (ab > best_bits) { best_bits = ab; best_k = k; best_u = p; }
                 }
@@ -342,8 +373,16 @@ hsq_search_tc_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_
                 aux[6] = __uint_as_float(mask0);
                 aux[7] = thr;
             }
-            search_epilogue<uint8_t>(valid, c, best_k, best_u, codes, u_out, seg_start, n_seg, minmax_keys);
+            if (valid) {
+                codes[c] = (uint8_t)best_k;
+                u_out[c] = best_u;
+            }
+            if (minmax_keys != nullptr) {
+                const int seg = valid ? cached_segment(segc, seg_start, n_seg, c) : -1;
+                minmax_add_warp(mm, valid, seg, best_u, minmax_keys);
+            }
         }
+        if (minmax_keys != nullptr) minmax_flush_warp(mm, minmax_keys);
     }
 
     tc_fence_before();
@@ -443,7 +482,7 @@ int hsq_search_tc_dbg(const float *grad, int64_t n_chunks, const float *codebook
     int flags = 0;
     if (const char *f = getenv("GQ_TC_FLAGS")) flags = atoi(f);
     tc::hsq_search_tc_kernel<<<grid, tc::kThreads, tc::kSmemBytes, st>>>(
-        mg, mc, n_chunks, (uint8_t *)codes, u_out, seg_start, n_seg, minmax_keys, dbg_scores, dbg_tiles, flags);
+        mg, mc, codebook, n_chunks, (uint8_t *)codes, u_out, seg_start, n_seg, minmax_keys, dbg_scores, dbg_tiles, flags);
     GQ_LAUNCH_CHECK("hsq_search_tc");
     return GQ_OK;
 }

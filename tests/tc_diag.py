@@ -50,10 +50,10 @@ cbs = cb.copy()
 cs_true = cbs.astype(np.float64).sum(1)
 print("codeword row-sum off: %d" % (np.abs(aux[:, 5] - cs_true[gc]) > 1e-5).sum())
 masks = aux[:, 6].view(np.uint32)
-og = oc // 8
-in_mask = ((masks >> og.astype(np.uint32)) & 1).astype(bool)
+og = oc // 4
+in_mask = np.where(og < 32, ((masks >> (og % 32).astype(np.uint32)) & 1).astype(bool), True)
 print("oracle winner group missing from candidate mask: %d (of bad %d)   mean popcount %.3f" % ((~in_mask).sum(), (~in_mask & bad).sum(), np.mean([bin(m).count("1") for m in masks[:20000]])))
-print("bad with same group as oracle: %d / %d" % ((bad & ((gc // 8) == og)).sum(), bad.sum()))
+print("bad with same group as oracle: %d / %d" % ((bad & ((gc // 4) == og)).sum(), bad.sum()))
 if bad.any():
     its = aux[bad, 2].astype(int)
     print("local iteration histogram of bad chunks (it: count):", dict(zip(*np.unique(its, return_counts=True))))
