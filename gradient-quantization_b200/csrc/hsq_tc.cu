@@ -32,8 +32,9 @@ namespace tc {
 constexpr int kD = 16;
 constexpr int kK = 256;
 constexpr int kTileM = 128;
-constexpr int kStages = 4;
-constexpr int kThreads = 384;  // 4 control warps + 2 x 4 epilogue warps
+constexpr int kStages = 6;   // ring of smem stages AND of TMEM full/empty barriers: a multiple of 2 (TMEM
+                             // buffers) and of kEpiGroups, so each barrier is always waited on by the same warps
+constexpr int kMaxEpiGroups = 3;   // epilogue groups of 4 warps, round-robin over tiles (2 or 3)
 constexpr uint32_t kTileBytes = kTileM * kD * 4;  // 8192
 constexpr uint32_t kCbBytes = kK * kD * 4;        // 16384
 constexpr int kGroup = 4;                         // codewords per rescoring group
@@ -42,6 +43,7 @@ constexpr uint32_t kPlaneBytes = kK * 128;        // one rescoring plane: 128-by
 constexpr int kPlanes = 4;
 constexpr float kMargin = 3.0f / 512.0f;          // 2 * eps / ||v||
 
+static_assert(kStages % 2 == 0 && kStages % 3 == 0, "barrier ring must be a multiple of the buffer and group counts");
 constexpr uint32_t kOffA = 0;
 constexpr uint32_t kOffCb = kStages * kTileBytes;
 constexpr uint32_t kOffPlanes = kOffCb + kCbBytes;
@@ -76,12 +78,14 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
     return ok;
 }
 // bounded wait: a protocol bug traps (sticky error, process exits) instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, bool backoff = false)
 {
-    // each try_wait suspends the thread for a hardware time slice before it reports failure
+    // back off between polls so that waiting warps do not steal issue/ALU slots from the
+    // epilogue warps sharing their scheduler
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 24)) __trap();
+        if (backoff) __nanosleep(40);
+        if (++spins > (1u << 22)) __trap();
     }
 }
 
@@ -163,26 +167,28 @@ __device__ __forceinline__ float exact_score(const uint8_t *__restrict__ cw_base
     return acc;
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+template <int kEpiGroups, bool kDebug>
+__global__ void __launch_bounds__(128 + 128 * kEpiGroups, 1)
 hsq_search_tc_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_constant__ CUtensorMap map_cb,
                      const float *__restrict__ codebook, int64_t n_chunks, uint8_t *__restrict__ codes,
                      float *__restrict__ u_out,
                      const int64_t *__restrict__ seg_start, int n_seg, uint32_t *__restrict__ minmax_keys,
                      float *__restrict__ dbg_scores, int dbg_tiles, int flags)
 {
+    constexpr int kThreads = 128 + 128 * kEpiGroups;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned, still a shared pointer
     uint8_t *s_a = smem + kOffA;
     uint8_t *s_cb = smem + kOffCb;
     uint8_t *s_planes = smem + kOffPlanes;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kOffBar);
-    // barrier slots: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], cb_full
+    // barrier slots: full[kStages], empty[kStages], tmem_full[kStages], tmem_empty[kStages], cb_full
     const uint32_t bar_full = smem_u32(bars);
     const uint32_t bar_empty = bar_full + 8 * kStages;
     const uint32_t bar_tfull = bar_empty + 8 * kStages;
-    const uint32_t bar_tempty = bar_tfull + 16;
-    const uint32_t bar_cb = bar_tempty + 16;
-    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(smem + kOffBar + 8 * (2 * kStages + 5));
+    const uint32_t bar_tempty = bar_tfull + 8 * kStages;
+    const uint32_t bar_cb = bar_tempty + 8 * kStages;
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(smem + kOffBar + 8 * (4 * kStages + 1));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -197,7 +203,7 @@ hsq_search_tc_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_
             mbar_init(bar_full + 8 * s, 1);
             mbar_init(bar_empty + 8 * s, 4);   // one arrive per epilogue warp of the tile
         }
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < kStages; ++b) {
             mbar_init(bar_tfull + 8 * b, 1);
             mbar_init(bar_tempty + 8 * b, 4);
         }
@@ -228,7 +234,7 @@ hsq_search_tc_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_
             for (int it = 0; it < my_tiles; ++it) {
                 const int s = it % kStages;
                 const int64_t tile = tile0 + it;
-                mbar_wait(bar_empty + 8 * s, ((it / kStages) & 1) ^ 1);
+                mbar_wait(bar_empty + 8 * s, ((it / kStages) & 1) ^ 1, flags & 1);
                 mbar_expect_tx(bar_full + 8 * s, kTileBytes);
                 tma_load_2d(smem_u32(s_a + s * kTileBytes), &map_grad, bar_full + 8 * s, 0, (int)(tile * kTileM));
             }
@@ -241,19 +247,20 @@ hsq_search_tc_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_
             for (int it = 0; it < my_tiles; ++it) {
                 const int s = it % kStages;
                 const int b = it & 1;
-                mbar_wait(bar_tempty + 8 * b, ((it >> 1) & 1) ^ 1);   // epilogue drained this TMEM buffer
-                mbar_wait(bar_full + 8 * s, (it / kStages) & 1);      // TMA landed this tile
+                if (it >= 2)   // the epilogue of tile it-2 drained this TMEM buffer
+                    mbar_wait(bar_tempty + 8 * ((it - 2) % kStages), ((it - 2) / kStages) & 1, flags & 2);
+                mbar_wait(bar_full + 8 * s, (it / kStages) & 1, flags & 2);      // TMA landed this tile
                 tc_fence_after();
                 const uint64_t adesc = make_desc(smem_u32(s_a + s * kTileBytes));
                 const uint32_t taddr = tmem_base + (uint32_t)(b * kK);
                 mma_tf32(taddr, adesc, bdesc, 0u);              // k = 0..7   (bytes  0..31 of each row)
                 mma_tf32(taddr, adesc + 2, bdesc + 2, 1u);      // k = 8..15  (bytes 32..63): +32 B = +2 units
-                mma_commit(bar_tfull + 8 * b);
+                mma_commit(bar_tfull + 8 * s);
             }
         }
     } else if (warp >= 4) {
         // ----------------------------------------------------------- epilogue ---
-        const int egroup = (warp - 4) >> 2;   // 0: even local tiles (TMEM buffer 0), 1: odd
+        const int egroup = (warp - 4) >> 2;   // handles local tiles it = egroup (mod kEpiGroups)
         const int quad = warp & 3;            // TMEM lane quadrant this warp may read
         const int row = quad * 32 + lane;     // row of the tile == TMEM lane
         const int rot = (lane & 7) >> 1, hlf = lane & 1;
@@ -263,14 +270,14 @@ hsq_search_tc_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_
         for (int u = 0; u < 4; ++u) uo[u] = 16u * ((u + rot) & 3);
         SegCache segc;
         MinMaxAcc mm;
-        for (int it = egroup; it < my_tiles; it += 2) {
+        for (int it = egroup; it < my_tiles; it += kEpiGroups) {
             const int s = it % kStages;
             const int b = it & 1;
             const int64_t tile = tile0 + it;
             const int64_t c = tile * kTileM + row;
             const bool valid = c < n_chunks;
-            mbar_wait(bar_full + 8 * s, (it / kStages) & 1);   // TMA data visible to this thread
-            mbar_wait(bar_tfull + 8 * b, (it >> 1) & 1);       // accumulators complete
+            mbar_wait(bar_full + 8 * s, (it / kStages) & 1, flags & 4);   // TMA data visible to this thread
+            mbar_wait(bar_tfull + 8 * s, (it / kStages) & 1, flags & 4);  // accumulators complete
             __syncwarp();                                      // converged before .sync.aligned TMEM loads
             tc_fence_after();
 
@@ -282,7 +289,7 @@ hsq_search_tc_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_
                 uint32_t sc[32];
                 tmem_ld32(taddr + blk * 32, sc);
                 tmem_ld_wait();
-                if (dbg_scores != nullptr && tile < dbg_tiles) {
+                if (kDebug && dbg_scores != nullptr && tile < dbg_tiles) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
                         dbg_scores[(tile * kTileM + row) * kK + blk * 32 + j] = __uint_as_float(sc[j]);
@@ -296,7 +303,7 @@ hsq_search_tc_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_
             // TMEM buffer b may be overwritten by the MMA of local tile it + 2
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * s);
 
             // this row's chunk, from the (swizzled) smem tile
             float v[kD];
@@ -345,16 +352,25 @@ hsq_search_tc_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_
             while (cand) {
                 const int g = __ffsll((long long)cand) - 1;
                 cand &= cand - 1;
+                float p[kGroup];
 #pragma unroll
-                for (int i = 0; i < kGroup; ++i) {
-                    const int k = g * kGroup + i;
-                    const float p = exact_score(cw_base, uo, k, v);
-                    const int ab = __float_as_int(p) & 0x7fffffff;
-                    if (ab > best_bits) { best_bits = ab; best_k = k; best_u = p; }
+                for (int i = 0; i < kGroup; ++i) p[i] = exact_score(cw_base, uo, g * kGroup + i, v);
+                // group maximum first (3 FMNMX), one compare against the running best, and only a
+                // winning group pays for locating its first maximal codeword
+                const float gmax = fmaxf(fmaxf(fabsf(p[0]), fabsf(p[1])), fmaxf(fabsf(p[2]), fabsf(p[3])));
+                const int gb = __float_as_int(gmax);
+                const float psum = (p[0] + p[1]) + (p[2] + p[3]);   // NaN (or inf - inf) takes the slow path
+                const bool has_nan = psum != psum;
+                if (gb > best_bits || has_nan || (flags & 8)) {
+#pragma unroll
+                    for (int i = 0; i < kGroup; ++i) {
+                        const int ab = __float_as_int(p[i]) & 0x7fffffff;
+                        if (ab > best_bits) { best_bits = ab; best_k = g * kGroup + i; best_u = p[i]; }
+                    }
                 }
             }
             __syncwarp();
-            if (dbg_scores != nullptr && valid) {
+            if (kDebug && dbg_scores != nullptr && valid) {
                 float *aux = dbg_scores + (size_t)dbg_tiles * kTileM * kK + c * 24;
                 for (int j = 0; j < kD; ++j) aux[8 + j] = v[j];
                 aux[0] = v[0];
@@ -466,12 +482,6 @@ int hsq_search_tc_dbg(const float *grad, int64_t n_chunks, const float *codebook
     if (e) return e;
     e = tc::make_map(&mc, codebook, tc::kK, tc::kK);
     if (e) return e;
-    static bool attr_set = false;
-    if (!attr_set) {
-        GQ_CUDA(cudaFuncSetAttribute(tc::hsq_search_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)tc::kSmemBytes));
-        attr_set = true;
-    }
     const int64_t n_tiles = (n_chunks + tc::kTileM - 1) / tc::kTileM;
     int sms = sm_count();
     if (const char *g = getenv("GQ_TC_GRID")) {   // debugging aid: force few CTAs -> many tiles per CTA
@@ -481,8 +491,23 @@ int hsq_search_tc_dbg(const float *grad, int64_t n_chunks, const float *codebook
     const int grid = (int)(n_tiles < sms ? n_tiles : sms);
     int flags = 0;
     if (const char *f = getenv("GQ_TC_FLAGS")) flags = atoi(f);
-    tc::hsq_search_tc_kernel<<<grid, tc::kThreads, tc::kSmemBytes, st>>>(
-        mg, mc, codebook, n_chunks, (uint8_t *)codes, u_out, seg_start, n_seg, minmax_keys, dbg_scores, dbg_tiles, flags);
+    int groups = 3;   // measured on B200: 3 epilogue groups 75 us, 2 groups 80 us (ResNet-50 gradient)
+    if (const char *f = getenv("GQ_TC_GROUPS")) groups = atoi(f) == 2 ? 2 : 3;
+    const bool dbg = dbg_scores != nullptr;
+#define GQ_TC_LAUNCH(G, DBG)                                                                                   \
+    do {                                                                                                       \
+        auto kern = tc::hsq_search_tc_kernel<G, DBG>;                                                          \
+        GQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes)); \
+        kern<<<grid, 128 + 128 * G, tc::kSmemBytes, st>>>(mg, mc, codebook, n_chunks, (uint8_t *)codes, u_out, \
+                                                          seg_start, n_seg, minmax_keys, dbg_scores, dbg_tiles, \
+                                                          flags);                                              \
+    } while (0)
+    if (dbg) {
+        if (groups == 3) GQ_TC_LAUNCH(3, true); else GQ_TC_LAUNCH(2, true);
+    } else {
+        if (groups == 3) GQ_TC_LAUNCH(3, false); else GQ_TC_LAUNCH(2, false);
+    }
+#undef GQ_TC_LAUNCH
     GQ_LAUNCH_CHECK("hsq_search_tc");
     return GQ_OK;
 }

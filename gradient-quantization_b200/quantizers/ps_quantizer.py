@@ -1,7 +1,7 @@
 import torch
-import torch.distributed as dist
 
 from .. import _lib
+from . import exchange as xch
 from ._shared import QuantizerBase, feedback_scale
 
 
@@ -74,7 +74,7 @@ class PSQuantizer(QuantizerBase):
     def exchange(self):
         """All-gather the packed records: rank r's record is already in slot r."""
         if self.distributed:
-            dist.all_gather_into_tensor(self.plan.records.view(-1), self.plan.records[self.rank])
+            xch.ps_all_gather(self.plan.records, self.rank)
 
     def apply(self, uniforms=None):
         if self.plan is None:

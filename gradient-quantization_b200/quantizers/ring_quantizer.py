@@ -1,7 +1,7 @@
 import torch
-import torch.distributed as dist
 
 from .. import _lib
+from . import exchange as xch
 from ._shared import QuantizerBase, feedback_scale
 
 
@@ -30,7 +30,7 @@ class RingQuantizer(QuantizerBase):
         plan.gather(self._grads())
         if user != 0:
             if self.distributed:
-                dist.recv(plan.records[user - 1], src=user - 1)
+                xch.ring_receive_previous(plan.records, user)
             # grad += previous hop's decompressed running sum   (ring_quantizer.py:31-32)
             plan.decode(first_user=user - 1, n_users=1, mean=False, accumulate=True, out=plan.arena)
         n = plan.arena.numel()
@@ -44,8 +44,8 @@ class RingQuantizer(QuantizerBase):
                 self._scratch_buf = torch.empty_like(plan.arena)
             dec = plan.decode(first_user=user, n_users=1, mean=False, out=self._scratch_buf)
             _lib.call("gq_sub", _lib.ptr(plan.arena), _lib.ptr(dec), n, _lib.ptr(err), _lib.stream())
-        if self.distributed and user + 1 < self.world:
-            dist.send(plan.records[user], dst=user + 1)
+        if self.distributed:
+            xch.ring_send_next(plan.records, user, self.world)
 
     def _record_per_parameter(self, user, scale):
         for i, param in enumerate(self.parameters):
@@ -71,6 +71,6 @@ class RingQuantizer(QuantizerBase):
         plan = self.plan
         last = self.args.num_users - 1
         if self.distributed:
-            dist.broadcast(plan.records[last], src=last)
+            xch.ring_broadcast_last(plan.records, self.world)
         g = plan.decode(first_user=last, n_users=1, mean=False, out=plan.arena)
         self._set_grads_from(g)
