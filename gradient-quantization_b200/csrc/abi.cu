@@ -2,6 +2,7 @@
 // Argument validation, workspace carving and kernel dispatch only; the kernels
 // live in the other translation units.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "gq_internal.cuh"
@@ -67,7 +68,7 @@ size_t gq_hsq_encode_workspace_bytes(int64_t n_chunks, int d, int K, int n_seg)
 {
     (void)d; (void)K;
     size_t keys = align_up((size_t)(n_seg > 0 ? n_seg : 1) * 2 * sizeof(uint32_t), 256);
-    return keys + hsq_tc_workspace_bytes(n_chunks);
+    return keys + 256 /* grid barrier word */ + hsq_tc_workspace_bytes(n_chunks);
 }
 
 static int validate_group(const void *grad, int64_t n_chunks, int d, const void *codebook, int K,
@@ -154,14 +155,34 @@ int gq_hsq_encode(const float *grad, int64_t n_chunks, int d, const float *codeb
     cudaStream_t st = as_stream(stream);
     uint32_t *keys = reinterpret_cast<uint32_t *>(workspace);
     const size_t keys_bytes = align_up((size_t)n_seg * 2 * sizeof(uint32_t), 256);
+    uint32_t *barrier = reinterpret_cast<uint32_t *>((char *)workspace + keys_bytes);
+    const size_t head = keys_bytes + 256;
     int e = GQ_OK;
+    // Optional single-launch encode (search + grid barrier + norm quantization inside the
+    // persistent tcgen05 kernel).  Measured on B200 (ResNet-50 gradient): 93.7 us fused vs
+    // 80.5 + 9.7 us as two kernels -- the quantization tail runs at 512 threads/SM inside the
+    // persistent kernel -- so it is opt-in (GQ_TC_FUSED=1) until the tail is restructured.
+    static const bool want_fused = [] { const char *f = getenv("GQ_TC_FUSED"); return f && atoi(f) == 1; }();
+    const bool fused = want_fused && (n_bit != 32) && (l_bytes == 1) && (algo != GQ_ALGO_EXACT) && n_chunks > 0 &&
+                       hsq_tc_supported(d, K, code_bytes);
+    if (fused) {
+        e = validate_group(grad, n_chunks, d, codebook, K, seg_start, n_seg);
+        if (e) return e;
+        GQ_REQUIRE(codes && l && lbub && u_out, "null output pointer");
+        GQ_REQUIRE(n_bit <= 7, "uint8 norm codes need n_bit <= 7 (levels 0..2^n)");
+        GQ_REQUIRE(((uintptr_t)grad & 15) == 0, "gradient must be 16-byte aligned");
+        e = launch_minmax_init(keys, n_seg, st, barrier);
+        if (e) return e;
+        return hsq_encode_tc_fused(grad, n_chunks, codebook, codes, u_out, seg_start, n_seg, keys, barrier, n_bit,
+                                   random, uniforms, philox_seed, philox_offset, (uint8_t *)l, lbub, st);
+    }
     if (n_bit != 32) {
         e = launch_minmax_init(keys, n_seg, st);
         if (e) return e;
     }
     e = gq_hsq_search(grad, n_chunks, d, codebook, K, codes, code_bytes, u_out, seg_start, n_seg,
-                      n_bit != 32 ? keys : nullptr, (char *)workspace + keys_bytes,
-                      workspace_bytes - keys_bytes, algo, stream);
+                      n_bit != 32 ? keys : nullptr, (char *)workspace + head, workspace_bytes - head, algo,
+                      stream);
     if (e) return e;
     if (n_bit == 32) return GQ_OK;
     return gq_norm_quantize(u_out, n_chunks, seg_start, n_seg, n_bit, random, uniforms, philox_seed,

@@ -5,7 +5,7 @@
 namespace gq {
 
 // hsq_exact.cu
-int launch_minmax_init(uint32_t *keys, int n_seg, cudaStream_t st);
+int launch_minmax_init(uint32_t *keys, int n_seg, cudaStream_t st, uint32_t *barrier = nullptr);
 int hsq_search_exact(const float *grad, int64_t n_chunks, int d, const float *codebook, int K,
                      void *codes, int code_bytes, float *u_out, const int64_t *seg_start, int n_seg,
                      uint32_t *minmax_keys, cudaStream_t st);
@@ -16,6 +16,13 @@ size_t hsq_tc_workspace_bytes(int64_t n_chunks);
 int hsq_search_tc(const float *grad, int64_t n_chunks, int d, const float *codebook, int K,
                   void *codes, int code_bytes, float *u_out, const int64_t *seg_start, int n_seg,
                   uint32_t *minmax_keys, void *workspace, size_t workspace_bytes, cudaStream_t st);
+
+// hsq_tc.cu: search + grid barrier + n-bit norm quantization in ONE persistent kernel
+// (keys must have been initialised and *barrier zeroed by launch_minmax_init before)
+int hsq_encode_tc_fused(const float *grad, int64_t n_chunks, const float *codebook, void *codes, float *u_out,
+                        const int64_t *seg_start, int n_seg, uint32_t *minmax_keys, uint32_t *barrier,
+                        int n_bit, int random, const float *uniforms, uint64_t seed, uint64_t offset,
+                        uint8_t *l, float *lbub, cudaStream_t st);
 
 // hsq_tail.cu
 int launch_seg_minmax(const float *u, int64_t n, const int64_t *seg_start, int n_seg, uint32_t *keys,
@@ -64,6 +71,88 @@ __device__ __forceinline__ void search_epilogue(bool valid, int64_t c, int best_
     }
 }
 
+
+// n-bit norm quantization of u[i_begin, i_end) by `nthreads` cooperating threads (thread `tid`):
+// four consecutive chunks per thread and iteration (float4 of u, one Philox block, one packed
+// store).  i_begin must be a multiple of 4.  keys hold the per-tensor min/max (ordered-uint form).
+// Shared by norm_quantize_kernel and the fused tail of the tcgen05 search kernel.
+template <typename LT, bool VOLATILE_KEYS>
+__device__ __forceinline__ void quantize_range(const float *__restrict__ u, int64_t i_begin, int64_t i_end,
+                                               int64_t n, int tid, int nthreads,
+                                               const int64_t *__restrict__ seg_start, int n_seg, float s,
+                                               int random, const float *__restrict__ uniforms, uint64_t seed,
+                                               uint64_t offset, LT *__restrict__ l, const uint32_t *keys)
+{
+    SegCache segc;
+    float lb = 0.0f, ub = 0.0f;
+    int cur = -1;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(u) & 15) == 0) &&
+                         (uniforms == nullptr || (reinterpret_cast<uintptr_t>(uniforms) & 15) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(l) & (4 * sizeof(LT) - 1)) == 0);
+    for (int64_t i0 = i_begin + 4 * (int64_t)tid; i0 < i_end; i0 += 4 * (int64_t)nthreads) {
+        const int64_t q = i0 >> 2;
+        const bool full = aligned && (i0 + 3 < n);
+        float x[4], r[4] = {0.f, 0.f, 0.f, 0.f};
+        if (full) {
+            const float4 t = VOLATILE_KEYS ? __ldcg(reinterpret_cast<const float4 *>(u) + q)
+                                           : __ldg(reinterpret_cast<const float4 *>(u) + q);
+            x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w;
+        } else {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) x[t] = (i0 + t < n) ? u[i0 + t] : 0.0f;
+        }
+        if (random) {
+            if (uniforms) {
+                if (full) {
+                    const float4 t = __ldg(reinterpret_cast<const float4 *>(uniforms) + q);
+                    r[0] = t.x; r[1] = t.y; r[2] = t.z; r[3] = t.w;
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) r[t] = (i0 + t < n) ? uniforms[i0 + t] : 0.0f;
+                }
+            } else if (((offset + (uint64_t)i0) & 3u) == 0) {
+                const uint4 w = philox4x32_10(seed, (offset + (uint64_t)i0) >> 2);
+                r[0] = u01(w.x); r[1] = u01(w.y); r[2] = u01(w.z); r[3] = u01(w.w);
+            } else {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) r[t] = philox_uniform(seed, offset, (uint64_t)(i0 + t));
+            }
+        }
+        int lv[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int64_t i = i0 + t;
+            if (i < n) {
+                const int seg = cached_segment(segc, seg_start, n_seg, i);
+                if (seg != cur) {
+                    cur = seg;
+                    if (VOLATILE_KEYS) {
+                        lb = key_to_float(__ldcg(keys + 2 * seg));
+                        ub = key_to_float(__ldcg(keys + 2 * seg + 1));
+                    } else {
+                        lb = key_to_float(__ldg(keys + 2 * seg));
+                        ub = key_to_float(__ldg(keys + 2 * seg + 1));
+                    }
+                }
+                lv[t] = psc_level(x[t], lb, ub, s, random, r[t]);
+            } else {
+                lv[t] = 0;
+            }
+        }
+        if (full) {
+            if (sizeof(LT) == 1) {
+                reinterpret_cast<uint32_t *>(l)[q] =
+                    (uint32_t)lv[0] | ((uint32_t)lv[1] << 8) | ((uint32_t)lv[2] << 16) | ((uint32_t)lv[3] << 24);
+            } else {
+                reinterpret_cast<int4 *>(l)[q] = make_int4(lv[0], lv[1], lv[2], lv[3]);
+            }
+        } else {
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                if (i0 + t < n) l[i0 + t] = (LT)lv[t];
+        }
+    }
+}
 
 // Running per-tensor min/max of u kept in registers while a warp walks CONSECUTIVE chunks
 // (the tcgen05 kernel gives every CTA a contiguous range of tiles): one atomic pair per warp

@@ -164,18 +164,19 @@ hsq_search_generic_kernel(const float *__restrict__ grad, int64_t n_chunks, int 
     }
 }
 
-__global__ void minmax_init_kernel(uint32_t *keys, int n_seg)
+__global__ void minmax_init_kernel(uint32_t *keys, int n_seg, uint32_t *barrier)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && barrier != nullptr) *barrier = 0u;
     if (i < n_seg) {
         keys[2 * i] = GQ_KEY_MIN_INIT;
         keys[2 * i + 1] = GQ_KEY_MAX_INIT;
     }
 }
 
-int launch_minmax_init(uint32_t *keys, int n_seg, cudaStream_t st)
+int launch_minmax_init(uint32_t *keys, int n_seg, cudaStream_t st, uint32_t *barrier)
 {
-    minmax_init_kernel<<<(n_seg + 127) / 128, 128, 0, st>>>(keys, n_seg);
+    minmax_init_kernel<<<(n_seg + 127) / 128, 128, 0, st>>>(keys, n_seg, barrier);
     GQ_LAUNCH_CHECK("minmax_init");
     return GQ_OK;
 }

@@ -7,7 +7,7 @@
 //        ring_quantizer.py:31-32)
 // All HBM-bound.  Algorithmic bytes per gradient element (d = chunk dim, U users):
 //   quantize: (4 u + 1 l [+4 r]) / d        decode-reduce: 4 + 2U/d (+4 if accumulate)
-#include "gq_common.cuh"
+#include "gq_internal.cuh"
 
 namespace gq {
 
@@ -52,70 +52,8 @@ norm_quantize_kernel(const float *__restrict__ u, int64_t n, const int64_t *__re
     if (blockIdx.x == 0) {
         for (int i = threadIdx.x; i < 2 * n_seg; i += 256) lbub[i] = key_to_float(keys[i]);
     }
-    SegCache segc;
-    float lb = 0.0f, ub = 0.0f;
-    int cur = -1;
-    const int64_t n4 = (n + 3) / 4;
-    const bool aligned = ((reinterpret_cast<uintptr_t>(u) & 15) == 0) &&
-                         (uniforms == nullptr || (reinterpret_cast<uintptr_t>(uniforms) & 15) == 0) &&
-                         ((reinterpret_cast<uintptr_t>(l) & (4 * sizeof(LT) - 1)) == 0);
-    for (int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x; q < n4; q += (int64_t)gridDim.x * 256) {
-        const int64_t i0 = q * 4;
-        const bool full = aligned && (i0 + 3 < n);
-        float x[4], r[4] = {0.f, 0.f, 0.f, 0.f};
-        if (full) {
-            const float4 t = __ldg(reinterpret_cast<const float4 *>(u) + q);
-            x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w;
-        } else {
-#pragma unroll
-            for (int t = 0; t < 4; ++t) x[t] = (i0 + t < n) ? u[i0 + t] : 0.0f;
-        }
-        if (random) {
-            if (uniforms) {
-                if (full) {
-                    const float4 t = __ldg(reinterpret_cast<const float4 *>(uniforms) + q);
-                    r[0] = t.x; r[1] = t.y; r[2] = t.z; r[3] = t.w;
-                } else {
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) r[t] = (i0 + t < n) ? uniforms[i0 + t] : 0.0f;
-                }
-            } else if (((offset + (uint64_t)i0) & 3u) == 0) {
-                const uint4 w = philox4x32_10(seed, (offset + (uint64_t)i0) >> 2);
-                r[0] = u01(w.x); r[1] = u01(w.y); r[2] = u01(w.z); r[3] = u01(w.w);
-            } else {
-#pragma unroll
-                for (int t = 0; t < 4; ++t) r[t] = philox_uniform(seed, offset, (uint64_t)(i0 + t));
-            }
-        }
-        int lv[4];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const int64_t i = i0 + t;
-            if (i < n) {
-                const int seg = cached_segment(segc, seg_start, n_seg, i);
-                if (seg != cur) {
-                    cur = seg;
-                    lb = key_to_float(__ldg(keys + 2 * seg));
-                    ub = key_to_float(__ldg(keys + 2 * seg + 1));
-                }
-                lv[t] = psc_level(x[t], lb, ub, s, random, r[t]);
-            } else {
-                lv[t] = 0;
-            }
-        }
-        if (full) {
-            if (sizeof(LT) == 1) {
-                reinterpret_cast<uint32_t *>(l)[q] =
-                    (uint32_t)lv[0] | ((uint32_t)lv[1] << 8) | ((uint32_t)lv[2] << 16) | ((uint32_t)lv[3] << 24);
-            } else {
-                reinterpret_cast<int4 *>(l)[q] = make_int4(lv[0], lv[1], lv[2], lv[3]);
-            }
-        } else {
-#pragma unroll
-            for (int t = 0; t < 4; ++t)
-                if (i0 + t < n) l[i0 + t] = (LT)lv[t];
-        }
-    }
+    quantize_range<LT, false>(u, 0, n, n, (int)(blockIdx.x * 256 + threadIdx.x), (int)(gridDim.x * 256), seg_start,
+                              n_seg, s, random, uniforms, seed, offset, l, keys);
 }
 
 template <typename LT>

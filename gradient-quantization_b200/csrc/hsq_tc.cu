@@ -167,13 +167,25 @@ __device__ __forceinline__ float exact_score(const uint8_t *__restrict__ cw_base
     return acc;
 }
 
+// Optional fused tail: after a grid-wide barrier (all CTAs are resident: grid <= SM count,
+// 1 CTA/SM) every CTA quantizes the norms of its own chunk range, so encode is ONE launch.
+struct TcTail {
+    uint8_t *l;              // nullptr = search only
+    float *lbub;
+    uint32_t *barrier;       // zeroed before the launch
+    const float *uniforms;
+    uint64_t seed, offset;
+    float s;                 // 2^n_bit
+    int random;
+};
+
 template <int kEpiGroups, bool kDebug>
 __global__ void __launch_bounds__(128 + 128 * kEpiGroups, 1)
 hsq_search_tc_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_constant__ CUtensorMap map_cb,
                      const float *__restrict__ codebook, int64_t n_chunks, uint8_t *__restrict__ codes,
                      float *__restrict__ u_out,
                      const int64_t *__restrict__ seg_start, int n_seg, uint32_t *__restrict__ minmax_keys,
-                     float *__restrict__ dbg_scores, int dbg_tiles, int flags)
+                     float *__restrict__ dbg_scores, int dbg_tiles, int flags, const TcTail tail)
 {
     constexpr int kThreads = 128 + 128 * kEpiGroups;
     extern __shared__ uint8_t smem_raw[];
@@ -407,6 +419,28 @@ hsq_search_tc_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_
     if (warp == 2) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
     }
+    if (tail.l != nullptr) {
+        // grid barrier: every CTA's min/max atomics are performed before anyone reads lb/ub
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(tail.barrier, 1u);
+            uint32_t spins = 0;
+            while (*reinterpret_cast<volatile uint32_t *>(tail.barrier) < gridDim.x) {
+                __nanosleep(64);
+                if (++spins > (1u << 24)) __trap();
+            }
+            __threadfence();
+        }
+        __syncthreads();
+        if (blockIdx.x == 0) {
+            for (int i = threadIdx.x; i < 2 * n_seg; i += kThreads) tail.lbub[i] = key_to_float(__ldcg(minmax_keys + i));
+        }
+        const int64_t c_begin = tile0 * kTileM;
+        const int64_t c_end = min((tile0 + my_tiles) * (int64_t)kTileM, n_chunks);
+        quantize_range<uint8_t, true>(u_out, c_begin, c_end, n_chunks, (int)threadIdx.x, kThreads, seg_start, n_seg,
+                                      tail.s, tail.random, tail.uniforms, tail.seed, tail.offset, tail.l,
+                                      minmax_keys);
+    }
 }
 
 // ------------------------------------------------------------------ host side ---
@@ -471,9 +505,9 @@ bool hsq_tc_supported(int d, int K, int code_bytes)
 
 size_t hsq_tc_workspace_bytes(int64_t) { return 0; }
 
-int hsq_search_tc_dbg(const float *grad, int64_t n_chunks, const float *codebook, void *codes, float *u_out,
-                      const int64_t *seg_start, int n_seg, uint32_t *minmax_keys, float *dbg_scores,
-                      int dbg_tiles, cudaStream_t st)
+static int launch_tc(const float *grad, int64_t n_chunks, const float *codebook, void *codes, float *u_out,
+                     const int64_t *seg_start, int n_seg, uint32_t *minmax_keys, float *dbg_scores,
+                     int dbg_tiles, const tc::TcTail &tail, cudaStream_t st)
 {
     GQ_REQUIRE(((uintptr_t)grad & 15) == 0 && ((uintptr_t)codebook & 15) == 0, "TMA needs 16-byte aligned bases");
     GQ_REQUIRE(n_chunks < ((int64_t)1 << 31) - 256, "n_chunks too large for one tensor map");
@@ -500,7 +534,7 @@ int hsq_search_tc_dbg(const float *grad, int64_t n_chunks, const float *codebook
         GQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes)); \
         kern<<<grid, 128 + 128 * G, tc::kSmemBytes, st>>>(mg, mc, codebook, n_chunks, (uint8_t *)codes, u_out, \
                                                           seg_start, n_seg, minmax_keys, dbg_scores, dbg_tiles, \
-                                                          flags);                                              \
+                                                          flags, tail);                                        \
     } while (0)
     if (dbg) {
         if (groups == 3) GQ_TC_LAUNCH(3, true); else GQ_TC_LAUNCH(2, true);
@@ -510,6 +544,32 @@ int hsq_search_tc_dbg(const float *grad, int64_t n_chunks, const float *codebook
 #undef GQ_TC_LAUNCH
     GQ_LAUNCH_CHECK("hsq_search_tc");
     return GQ_OK;
+}
+
+int hsq_search_tc_dbg(const float *grad, int64_t n_chunks, const float *codebook, void *codes, float *u_out,
+                      const int64_t *seg_start, int n_seg, uint32_t *minmax_keys, float *dbg_scores,
+                      int dbg_tiles, cudaStream_t st)
+{
+    tc::TcTail tail = {};
+    return launch_tc(grad, n_chunks, codebook, codes, u_out, seg_start, n_seg, minmax_keys, dbg_scores, dbg_tiles,
+                     tail, st);
+}
+
+int hsq_encode_tc_fused(const float *grad, int64_t n_chunks, const float *codebook, void *codes, float *u_out,
+                        const int64_t *seg_start, int n_seg, uint32_t *minmax_keys, uint32_t *barrier,
+                        int n_bit, int random, const float *uniforms, uint64_t seed, uint64_t offset,
+                        uint8_t *l, float *lbub, cudaStream_t st)
+{
+    tc::TcTail tail = {};
+    tail.l = l;
+    tail.lbub = lbub;
+    tail.barrier = barrier;
+    tail.uniforms = uniforms;
+    tail.seed = seed;
+    tail.offset = offset;
+    tail.s = (float)(1u << n_bit);
+    tail.random = random;
+    return launch_tc(grad, n_chunks, codebook, codes, u_out, seg_start, n_seg, minmax_keys, nullptr, 0, tail, st);
 }
 
 int hsq_search_tc(const float *grad, int64_t n_chunks, int d, const float *codebook, int K, void *codes,
