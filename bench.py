@@ -42,6 +42,25 @@ def make_args(num_users):
                            two_phase=False, mode="ps", scale="exp", num_users=num_users)
 
 
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the search kernel from the committed
+    `ncu --set full` capture (profiles/), per launch; None if the summary is missing."""
+    import csv
+    import glob
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_prof_tc_*_summary.csv"))):
+        rd = wr = None
+        with open(path) as fh:
+            for row in csv.reader(fh):
+                if len(row) >= 3 and row[0] == "dram__bytes_read.sum":
+                    rd = float(row[2]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}.get(row[1], 1.0)
+                if len(row) >= 3 and row[0] == "dram__bytes_write.sum":
+                    wr = float(row[2]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}.get(row[1], 1.0)
+        if rd is not None and wr is not None:
+            best = (rd + wr, os.path.basename(path))
+    return best
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -307,27 +326,64 @@ def main():
     encode_ms = time_loop(lambda i: plan.encode(rank, src=inputs[i % ROT]), K)
 
     # ---- end to end through the public quantizer API with HOST buffers ----
+    # Every step copies its gradient from pinned host memory (H2D) and reads the averaged gradient
+    # back to pinned host memory (D2H).  The three stages are software-pipelined over two device
+    # buffers: H2D of step i+1 and D2H of step i-1 overlap the codec work of step i (PCIe is full
+    # duplex), which is how a training loop would feed it.
     host_in = [torch.empty(plan.arena_elems, dtype=torch.float32).pin_memory() for _ in range(2)]
     for h in host_in:
         h.copy_(inputs[0].cpu())
-    host_out = torch.empty(plan.arena_elems, dtype=torch.float32).pin_memory()
-    for p, v in zip(params, plan.views()):
-        p.grad = v                                   # gradients live in the arena: gather is free
+    host_out = [torch.empty(plan.arena_elems, dtype=torch.float32).pin_memory() for _ in range(2)]
+    dev_in = [torch.empty(plan.arena_elems, device=dev) for _ in range(2)]
+    dev_out = [torch.empty(plan.arena_elems, device=dev) for _ in range(2)]
+    s_h2d, s_d2h = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream()
+    ev_in = [torch.cuda.Event() for _ in range(2)]
+    ev_in_free = [torch.cuda.Event() for _ in range(2)]
+    ev_out = [torch.cuda.Event() for _ in range(2)]
+    ev_out_free = [torch.cuda.Event() for _ in range(2)]
+
+    def issue_h2d(i):
+        b = i % 2
+        with torch.cuda.stream(s_h2d):
+            s_h2d.wait_event(ev_in_free[b])
+            dev_in[b].copy_(host_in[b], non_blocking=True)
+            ev_in[b].record(s_h2d)
 
     def e2e_step(i):
-        plan.arena.copy_(host_in[i % 2], non_blocking=True)      # H2D of this step's gradient
-        q.record(rank, epoch=1)                                   # public API: encode
+        b = i % 2
+        main.wait_event(ev_in[b])
+        for p, v in zip(params, plan.views(dev_in[b])):
+            p.grad = v                                            # this step's gradient (device views)
+        q.record(rank, epoch=1)                                   # public API: gather + fused encode
+        ev_in_free[b].record(main)
         q.apply()                                                 # all-gather + decode-and-average
-        host_out.copy_(plan.arena, non_blocking=True)             # D2H of the averaged gradient
+        main.wait_event(ev_out_free[b])
+        dev_out[b].copy_(plan.arena, non_blocking=True)
+        ev_out[b].record(main)
+        with torch.cuda.stream(s_d2h):
+            s_d2h.wait_event(ev_out[b])
+            host_out[b].copy_(dev_out[b], non_blocking=True)      # D2H of the averaged gradient
+            ev_out_free[b].record(s_d2h)
 
-    KE = max(min(K, 20), 3)
-    for i in range(2):
-        e2e_step(i)
+    for b in range(2):
+        ev_in_free[b].record(main)
+        ev_out_free[b].record(main)
+    KE = max(min(K, 20), 4)
+
+    def e2e_loop(n):
+        issue_h2d(0)
+        for i in range(n):
+            if i + 1 < n:
+                issue_h2d(i + 1)
+            e2e_step(i)
+        main.wait_stream(s_d2h)
+
+    e2e_loop(3)
     barrier()
     b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     b0.record()
-    for i in range(KE):
-        e2e_step(i)
+    e2e_loop(KE)
     b1.record()
     barrier()
     e2e_ms = b0.elapsed_time(b1)
@@ -337,6 +393,8 @@ def main():
         e2e_ms = t.item()
     e2e_ms /= KE
     e2e_value = world * n_total / (e2e_ms * 1e-3)
+    for p, v in zip(params, plan.views()):
+        p.grad = v
 
     # keep the same loop running until the sampler has seen the clocks under load
     t_end = time.time() + 0.6
@@ -357,6 +415,7 @@ def main():
         return
 
     peaks, peak_kind = measured_peaks()
+    traffic = ncu_traffic_bytes()
     hbm_peak = float(peaks["hbm_gbs"])
     # algorithmic bytes of the search kernel: read 4 B/elem, write 1 B code + 4 B u per chunk
     # (the 1-byte norm code is written by the quantize kernel from u; BASELINE.md counts
@@ -366,7 +425,8 @@ def main():
     alg_bytes_step = n_total * (8 + 2.0 * (world + 1) / 16)
     roofline = {
         "bound": "hbm", "kernel": "hsq_search (%s)" % a.algo, "achieved": achieved, "peak": hbm_peak,
-        "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_kind,
+        "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic[0] if traffic else None,
+        "traffic_source": traffic[1] if traffic else None, "peak_source": peak_kind,
         "kernel_ms": search_ms, "algorithmic_bytes_per_launch": alg_bytes_search,
         "tensor_flops_per_launch": 2.0 * g_hsq.K * g_hsq.n,
         "tensor_tflops_achieved": 2.0 * g_hsq.K * g_hsq.n / (search_ms * 1e-3) / 1e12,
@@ -386,7 +446,9 @@ def main():
         "roofline": roofline,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": plan.arena_elems * 4, "d2h_bytes_per_step": plan.arena_elems * 4,
-                "api": "PSQuantizer.record(rank)/apply() with pinned host gradient in and averaged gradient out"},
+                "api": "PSQuantizer.record(rank)/apply() on gradients copied from pinned host memory each step, "
+                       "averaged gradient copied back to pinned host memory each step",
+                "pipelining": "double-buffered: H2D of step i+1 and D2H of step i-1 overlap step i"},
         "gpu_launches": K * (plan.launches_per_encode() - 1 + plan.launches_per_decode(world)),
         "clocks": clocks,
     }
