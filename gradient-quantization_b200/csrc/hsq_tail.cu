@@ -269,13 +269,24 @@ hsq_decode_reduce_generic_kernel(const CodeT *__restrict__ codes, const LT *__re
     }
 }
 
-// Power-of-two chunk sizes (D = 4, 8, 16), up to MAXU users: one warp owns 128 consecutive
-// chunks per iteration.  Lane L loads the code / level bytes of chunks L, L+32, L+64, L+96 for
-// every user up front (all requests in flight together, four coalesced 32-byte requests per
-// array and user), then walks the 4*D4 rows of 32 float4: the chunk of row r, lane L is
-// q = (32 r + L) / D4, its owner lane is q % 32 and its slot q / 32 = r / D4 is the same for
-// the whole warp, so (code, norm) arrive with two shuffles from statically indexed registers.
-// Rows are finished one at a time (4 accumulator registers), users innermost in user order.
+// Power-of-two chunk sizes (D = 4, 8, 16): one warp owns 128 consecutive chunks per iteration,
+// handled as four slots of 32 chunks (lane <-> chunk).  Per slot the code / level bytes of ALL
+// users are loaded first (2U coalesced 32-byte requests in flight), the U norms are dequantized
+// once, and the warp then writes the D4 rows of 32 float4 of that slot: the chunk of row r,
+// lane L is q = (32 r + L) / D4 and lives in lane q of the slot, so (code, norm) arrive with
+// two shuffles per user from statically indexed registers.  Users are summed in user order with
+// separately rounded products (two packed mul.f32x2 per float4) and sums.
+// Register use is independent of the number of users beyond the MAXU * 2 slot registers.
+__device__ __forceinline__ float2 mul2(float2 a, float b)
+{
+    float2 r;
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %4};\n\t"
+        "mul.rn.f32x2 rd, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b));
+    return r;
+}
 template <int D, int MAXU, typename CodeT, typename LT>
 __global__ void __launch_bounds__(kDecodeThreads)
 hsq_decode_reduce_warp_kernel(const CodeT *__restrict__ codes, const LT *__restrict__ l,
@@ -298,80 +309,69 @@ hsq_decode_reduce_warp_kernel(const CodeT *__restrict__ codes, const LT *__restr
     const bool pow2 = (n_users & (n_users - 1)) == 0;
     const float inv_nu = 1.0f / nu;
     SegCache segc;
-    const int64_t n_iter = (n_chunks + 127) / 128;
+    const int64_t n_slots = (n_chunks + 31) / 32;
     const int64_t n4 = n_chunks * D4;
     float4 *o4 = reinterpret_cast<float4 *>(out);
-    for (int64_t itx = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5); itx < n_iter;
-         itx += (int64_t)gridDim.x * kWarps) {
-        const int64_t c0 = itx * 128;
-        int code[MAXU][4];
-        float nrm[MAXU][4];   // raw level (as float) or fp32 norm; dequantized below
+    for (int64_t slot = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5); slot < n_slots;
+         slot += (int64_t)gridDim.x * kWarps) {
+        const int64_t c = slot * 32 + lane;
+        const bool ok = c < n_chunks;
+        int code[MAXU];
+        float nrm[MAXU];
 #pragma unroll
         for (int u = 0; u < MAXU; ++u) {
-            if (u < n_users) {
-                const CodeT *cu = reinterpret_cast<const CodeT *>(reinterpret_cast<const char *>(codes) + u * user_stride);
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const int64_t c = c0 + t * 32 + lane;
-                    code[u][t] = (c < n_chunks) ? (int)cu[c] : 0;
-                }
+            code[u] = 0;
+            nrm[u] = 0.0f;
+            if (u < n_users && ok) {
+                const char *cu = reinterpret_cast<const char *>(codes) + u * user_stride;
+                code[u] = (int)reinterpret_cast<const CodeT *>(cu)[c];
                 if (n_bit == 32) {
-                    const float *nf = reinterpret_cast<const float *>(reinterpret_cast<const char *>(norms_f32) + u * user_stride);
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        const int64_t c = c0 + t * 32 + lane;
-                        nrm[u][t] = (c < n_chunks) ? nf[c] : 0.0f;
-                    }
+                    const char *nf = reinterpret_cast<const char *>(norms_f32) + u * user_stride;
+                    nrm[u] = reinterpret_cast<const float *>(nf)[c];
                 } else {
-                    const LT *lu = reinterpret_cast<const LT *>(reinterpret_cast<const char *>(l) + u * user_stride);
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        const int64_t c = c0 + t * 32 + lane;
-                        nrm[u][t] = (c < n_chunks) ? (float)(int)lu[c] : 0.0f;
-                    }
+                    const char *lu = reinterpret_cast<const char *>(l) + u * user_stride;
+                    nrm[u] = (float)(int)reinterpret_cast<const LT *>(lu)[c];
                 }
             }
         }
         if (n_bit != 32) {
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const int64_t c = c0 + t * 32 + lane;
-                const int seg = (c < n_chunks) ? cached_segment(segc, seg_start, n_seg, c) : 0;
-#pragma unroll
-                for (int u = 0; u < MAXU; ++u) {
-                    if (u < n_users) {
-                        const float *b = reinterpret_cast<const float *>(reinterpret_cast<const char *>(lbub) + u * user_stride);
-                        const float lb = __ldg(b + 2 * seg), ub = __ldg(b + 2 * seg + 1);
-                        // l * (ub - lb) / 2^n + lb   (probabilistic_scalar_compressor.py:31-32)
-                        nrm[u][t] = __fadd_rn(__fmul_rn(__fmul_rn(nrm[u][t], __fsub_rn(ub, lb)), inv_s), lb);
-                    }
-                }
-            }
-        }
-        const int64_t f0 = c0 * D4;
-#pragma unroll
-        for (int r = 0; r < 4 * D4; ++r) {
-            const int fl = r * 32 + lane;
-            const int owner = (fl / D4) & 31;
-            const int part = fl % D4;
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int seg = ok ? cached_segment(segc, seg_start, n_seg, c) : 0;
 #pragma unroll
             for (int u = 0; u < MAXU; ++u) {
                 if (u < n_users) {
-                    const int cd = __shfl_sync(0xffffffffu, code[u][r / D4], owner);
-                    const float nm = __shfl_sync(0xffffffffu, nrm[u][r / D4], owner);
+                    const float *b = reinterpret_cast<const float *>(reinterpret_cast<const char *>(lbub) + u * user_stride);
+                    const float lb = __ldg(b + 2 * seg), ub = __ldg(b + 2 * seg + 1);
+                    // l * (ub - lb) / 2^n + lb   (probabilistic_scalar_compressor.py:31-32)
+                    nrm[u] = __fadd_rn(__fmul_rn(__fmul_rn(nrm[u], __fsub_rn(ub, lb)), inv_s), lb);
+                }
+            }
+        }
+        const int64_t f0 = slot * 32 * D4;
+#pragma unroll
+        for (int r = 0; r < D4; ++r) {
+            const int fl = r * 32 + lane;
+            const int owner = fl / D4;
+            const int part = fl % D4;
+            float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < MAXU; ++u) {
+                if (u < n_users) {
+                    const int cd = __shfl_sync(0xffffffffu, code[u], owner);
+                    const float nm = __shfl_sync(0xffffffffu, nrm[u], owner);
                     const float4 cw = s_cbd[cd * D4 + part];
-                    float4 pr;
-                    pr.x = __fmul_rn(cw.x, nm); pr.y = __fmul_rn(cw.y, nm);
-                    pr.z = __fmul_rn(cw.z, nm); pr.w = __fmul_rn(cw.w, nm);
+                    const float2 p0 = mul2(make_float2(cw.x, cw.y), nm);
+                    const float2 p1 = mul2(make_float2(cw.z, cw.w), nm);
                     if (u == 0) {
-                        acc = pr;
+                        a0 = p0; a1 = p1;
                     } else {
-                        acc.x = __fadd_rn(acc.x, pr.x); acc.y = __fadd_rn(acc.y, pr.y);
-                        acc.z = __fadd_rn(acc.z, pr.z); acc.w = __fadd_rn(acc.w, pr.w);
+                        // scalar adds: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (one
+                        // rounding), which would break bit-exactness with the reference's mul-then-add
+                        a0.x = __fadd_rn(a0.x, p0.x); a0.y = __fadd_rn(a0.y, p0.y);
+                        a1.x = __fadd_rn(a1.x, p1.x); a1.y = __fadd_rn(a1.y, p1.y);
                     }
                 }
             }
+            float4 acc = make_float4(a0.x, a0.y, a1.x, a1.y);
             const int64_t f = f0 + fl;
             if (f < n4) {
                 if (mean && n_users > 1) {
@@ -405,7 +405,7 @@ static int launch_decode_warp(const void *codes, const void *l, const float *lbu
     GQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cb_bytes));
     int occ = 1;
     GQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kDecodeThreads, cb_bytes));
-    const int64_t iters = (n_chunks + 127) / 128;
+    const int64_t iters = (n_chunks + 31) / 32;
     const int64_t wblocks = (iters + kDecodeThreads / 32 - 1) / (kDecodeThreads / 32);
     int64_t cap = (int64_t)sm_count() * (occ < 1 ? 1 : occ);
     int grid = (int)(wblocks < cap ? wblocks : cap);

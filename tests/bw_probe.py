@@ -49,6 +49,16 @@ for U, mean in ((1, 0), (1, 1)):
                                     None, 0, U, n_chunks, 16, cb.data_ptr(), 256, seg.data_ptr(), 1, 6, mean, 0,
                                     bufs[i % 4].data_ptr(), _lib.stream()))
     print("decode U=%d mean=%d: %.4f ms  %.0f GB/s algorithmic" % (U, mean, ms, (N * 4 + n_chunks * 2) / ms / 1e6))
+# U users: records laid out with a common stride
+for U in (2, 4, 8):
+    stride = ((2 * n_chunks + 8 + 255) // 256) * 256
+    rec = torch.randint(0, 65, (U, stride), dtype=torch.uint8, device=dev)
+    rec[:, 2 * n_chunks:2 * n_chunks + 8] = torch.tensor([-0.05, 0.05], device=dev).view(torch.uint8).repeat(U, 1)
+    base = rec.data_ptr()
+    ms = timeit(lambda i: _lib.call("gq_hsq_decode_reduce", base, 1, base + n_chunks, 1, base + 2 * n_chunks, None, stride,
+                                    U, n_chunks, 16, cb.data_ptr(), 256, seg.data_ptr(), 1, 6, 1, 0,
+                                    bufs[i % 4].data_ptr(), _lib.stream()))
+    print("decode U=%d mean=1: %.4f ms  %.0f GB/s algorithmic" % (U, ms, (N * 4 + U * n_chunks * 2) / ms / 1e6))
 u = torch.randn(n_chunks, device=dev)
 lq = torch.empty(n_chunks, dtype=torch.uint8, device=dev)
 keys = torch.empty(2, dtype=torch.int32, device=dev)
