@@ -267,9 +267,8 @@ def main():
     outputs = [torch.empty(plan.arena_elems, device=dev) for _ in range(ROT)]
 
     def step(i):
-        plan.encode(rank, src=inputs[i % ROT])
-        q.exchange()
-        plan.decode(mean=True, out=outputs[i % ROT])
+        q.encode_local(rank, src=inputs[i % ROT])              # fused encode into the local packed record
+        q.exchange_and_decode(out=outputs[i % ROT])             # P2P barrier (or NCCL all-gather) + fused decode
 
     def barrier():
         if world > 1:
@@ -298,7 +297,7 @@ def main():
     # ---- per-kernel timing of the dominant kernel (HSQ search), same rotation ----
     st = _lib.stream()
     ws = plan.workspace
-    codes_ptr = plan.records[rank].data_ptr() + g_hsq.codes_off
+    codes_ptr = plan.records[0].data_ptr() + g_hsq.codes_off
 
     def search_only(i):
         _lib.call("gq_hsq_search", inputs[i % ROT].data_ptr() + g_hsq.arena_off * 4, g_hsq.n_chunks, g_hsq.dim,
@@ -307,7 +306,11 @@ def main():
                   args.hsq_algo, st)
 
     def decode_only(i):
-        plan.decode(mean=True, out=outputs[i % ROT])
+        if q.p2p is not None:
+            plan.decode(n_users=world, mean=True, out=outputs[i % ROT], base_ptr=q.p2p.user0_record_ptr(),
+                        user_offsets=q.p2p.user_offsets())
+        else:
+            plan.decode(mean=True, out=outputs[i % ROT])
 
     def time_loop(fn, iters):
         for i in range(3):
@@ -323,7 +326,7 @@ def main():
 
     search_ms = time_loop(search_only, K)
     decode_ms = time_loop(decode_only, K)
-    encode_ms = time_loop(lambda i: plan.encode(rank, src=inputs[i % ROT]), K)
+    encode_ms = time_loop(lambda i: plan.encode(0, src=inputs[i % ROT]), K)
 
     # ---- end to end through the public quantizer API with HOST buffers ----
     # Every step copies its gradient from pinned host memory (H2D) and reads the averaged gradient
@@ -441,6 +444,9 @@ def main():
                                "HSQ d=16 K=256 n=6, one user per GPU, ps encode+allgather+decode-mean",
                    "elements_per_user": n_total, "compressed_elements": plan.compressed_elems(),
                    "users": world, "wire_bytes_per_user": plan.wire_bytes(), "algo": a.algo,
+                   "exchange": ("none (1 user)" if world == 1 else
+                                ("peer-to-peer: barrier kernel + decode kernel reads peer records over NVLink"
+                                 if q.p2p is not None else "NCCL all-gather of packed records")),
                    "l2": "inputs/outputs rotate over %d buffers of %.0f MB each (> 126 MB L2)"
                          % (ROT, plan.arena_elems * 4 / 1e6)},
         "roofline": roofline,

@@ -209,9 +209,26 @@ int gq_hsq_decode_reduce(const void *codes, int code_bytes, const void *l, int l
     }
     GQ_REQUIRE(n_users == 1 || (user_stride_bytes % 4) == 0, "user stride must be a multiple of 4 bytes");
     GQ_REQUIRE(((uintptr_t)out & 15) == 0, "output must be 16-byte aligned");
-    return hsq_decode_reduce(codes, code_bytes, l, l_bytes, lbub, norms_f32, user_stride_bytes, n_users,
+    return hsq_decode_reduce(codes, code_bytes, l, l_bytes, lbub, norms_f32, user_stride_bytes, nullptr, n_users,
                              n_chunks, d, codebook, K, seg_start, n_seg, n_bit, mean, accumulate, out,
                              as_stream(stream));
+}
+
+int gq_hsq_decode_reduce_scattered(const void *codes, int code_bytes, const void *l, int l_bytes,
+                                   const float *lbub, const int64_t *user_byte_offsets, int n_users,
+                                   int64_t n_chunks, int d, const float *codebook, int K,
+                                   const int64_t *seg_start, int n_seg, int n_bit, int mean, int accumulate,
+                                   float *out, gq_stream_t stream)
+{
+    int e = validate_group(out, n_chunks, d, codebook, K, seg_start, n_seg);
+    if (e) return e;
+    GQ_REQUIRE(n_users >= 1 && n_users <= 8 && user_byte_offsets, "1..8 users with an offset table");
+    GQ_REQUIRE(code_bytes == 1 || code_bytes == 4, "code_bytes must be 1 or 4");
+    GQ_REQUIRE(n_bit >= 1 && n_bit <= 24 && l && lbub, "quantized norms required (n_bit 1..24)");
+    GQ_REQUIRE(l_bytes == 1 || l_bytes == 4, "l_bytes must be 1 or 4");
+    GQ_REQUIRE(((uintptr_t)out & 15) == 0, "output must be 16-byte aligned");
+    return hsq_decode_reduce(codes, code_bytes, l, l_bytes, lbub, nullptr, 0, user_byte_offsets, n_users, n_chunks,
+                             d, codebook, K, seg_start, n_seg, n_bit, mean, accumulate, out, as_stream(stream));
 }
 
 int gq_f32_reduce_users(const float *in, int64_t user_stride_bytes, int n_users, int64_t n, int mean,
@@ -219,8 +236,16 @@ int gq_f32_reduce_users(const float *in, int64_t user_stride_bytes, int n_users,
 {
     GQ_REQUIRE(n >= 0 && n_users >= 1, "bad sizes");
     GQ_REQUIRE(n == 0 || (in && out), "null pointer");
-    return launch_f32_reduce_users(in, user_stride_bytes, n_users, n, mean, accumulate, out,
+    return launch_f32_reduce_users(in, user_stride_bytes, nullptr, n_users, n, mean, accumulate, out,
                                    as_stream(stream));
+}
+
+int gq_f32_reduce_users_scattered(const float *in, const int64_t *user_byte_offsets, int n_users, int64_t n,
+                                  int mean, int accumulate, float *out, gq_stream_t stream)
+{
+    GQ_REQUIRE(n >= 0 && n_users >= 1 && n_users <= 8 && user_byte_offsets, "1..8 users with an offset table");
+    GQ_REQUIRE(n == 0 || (in && out), "null pointer");
+    return launch_f32_reduce_users(in, 0, user_byte_offsets, n_users, n, mean, accumulate, out, as_stream(stream));
 }
 
 int gq_axpy(const float *a, const float *b, float alpha, int64_t n, float *out, gq_stream_t stream)

@@ -32,12 +32,18 @@ int launch_norm_quantize(const float *u, int64_t n, const int64_t *seg_start, in
                          int l_bytes, float *lbub, const uint32_t *keys, cudaStream_t st);
 int launch_norm_dequantize(const void *l, int l_bytes, int64_t n, const int64_t *seg_start, int n_seg,
                            int n_bit, const float *lbub, float *out, cudaStream_t st);
+// byte offsets of each user's arrays relative to user 0's pointers (packed records need not be
+// equally spaced: with peer-to-peer exchange every user's record lives in a different GPU's memory)
+struct UserOffsets {
+    int64_t off[8];
+};
 int hsq_decode_reduce(const void *codes, int code_bytes, const void *l, int l_bytes, const float *lbub,
-                      const float *norms_f32, int64_t user_stride, int n_users, int64_t n_chunks, int d,
+                      const float *norms_f32, int64_t user_stride, const int64_t *user_offsets, int n_users,
+                      int64_t n_chunks, int d,
                       const float *codebook, int K, const int64_t *seg_start, int n_seg, int n_bit,
                       int mean, int accumulate, float *out, cudaStream_t st);
-int launch_f32_reduce_users(const float *in, int64_t user_stride, int n_users, int64_t n, int mean,
-                            int accumulate, float *out, cudaStream_t st);
+int launch_f32_reduce_users(const float *in, int64_t user_stride, const int64_t *user_offsets, int n_users,
+                            int64_t n, int mean, int accumulate, float *out, cudaStream_t st);
 int launch_axpy(const float *a, const float *b, float alpha, int64_t n, float *out, int sub,
                 cudaStream_t st);
 

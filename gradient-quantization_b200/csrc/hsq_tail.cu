@@ -291,7 +291,7 @@ template <int D, int MAXU, typename CodeT, typename LT>
 __global__ void __launch_bounds__(kDecodeThreads)
 hsq_decode_reduce_warp_kernel(const CodeT *__restrict__ codes, const LT *__restrict__ l,
                               const float *__restrict__ lbub, const float *__restrict__ norms_f32,
-                              int64_t user_stride, int n_users, int64_t n_chunks,
+                              const UserOffsets uoff, int n_users, int64_t n_chunks,
                               const float *__restrict__ codebook, int K,
                               const int64_t *__restrict__ seg_start, int n_seg, float s, int n_bit,
                               int mean, int accumulate, float *__restrict__ out)
@@ -323,13 +323,13 @@ hsq_decode_reduce_warp_kernel(const CodeT *__restrict__ codes, const LT *__restr
             code[u] = 0;
             nrm[u] = 0.0f;
             if (u < n_users && ok) {
-                const char *cu = reinterpret_cast<const char *>(codes) + u * user_stride;
+                const char *cu = reinterpret_cast<const char *>(codes) + uoff.off[u];
                 code[u] = (int)reinterpret_cast<const CodeT *>(cu)[c];
                 if (n_bit == 32) {
-                    const char *nf = reinterpret_cast<const char *>(norms_f32) + u * user_stride;
+                    const char *nf = reinterpret_cast<const char *>(norms_f32) + uoff.off[u];
                     nrm[u] = reinterpret_cast<const float *>(nf)[c];
                 } else {
-                    const char *lu = reinterpret_cast<const char *>(l) + u * user_stride;
+                    const char *lu = reinterpret_cast<const char *>(l) + uoff.off[u];
                     nrm[u] = (float)(int)reinterpret_cast<const LT *>(lu)[c];
                 }
             }
@@ -339,7 +339,7 @@ hsq_decode_reduce_warp_kernel(const CodeT *__restrict__ codes, const LT *__restr
 #pragma unroll
             for (int u = 0; u < MAXU; ++u) {
                 if (u < n_users) {
-                    const float *b = reinterpret_cast<const float *>(reinterpret_cast<const char *>(lbub) + u * user_stride);
+                    const float *b = reinterpret_cast<const float *>(reinterpret_cast<const char *>(lbub) + uoff.off[u]);
                     const float lb = __ldg(b + 2 * seg), ub = __ldg(b + 2 * seg + 1);
                     // l * (ub - lb) / 2^n + lb   (probabilistic_scalar_compressor.py:31-32)
                     nrm[u] = __fadd_rn(__fmul_rn(__fmul_rn(nrm[u], __fsub_rn(ub, lb)), inv_s), lb);
@@ -396,7 +396,7 @@ hsq_decode_reduce_warp_kernel(const CodeT *__restrict__ codes, const LT *__restr
 
 template <int D, int MAXU, typename CodeT, typename LT>
 static int launch_decode_warp(const void *codes, const void *l, const float *lbub, const float *norms_f32,
-                              int64_t user_stride, int n_users, int64_t n_chunks, const float *codebook,
+                              const UserOffsets &uoff, int n_users, int64_t n_chunks, const float *codebook,
                               int K, const int64_t *seg_start, int n_seg, float s, int n_bit, int mean,
                               int accumulate, float *out, cudaStream_t st)
 {
@@ -410,7 +410,7 @@ static int launch_decode_warp(const void *codes, const void *l, const float *lbu
     int64_t cap = (int64_t)sm_count() * (occ < 1 ? 1 : occ);
     int grid = (int)(wblocks < cap ? wblocks : cap);
     kern<<<grid < 1 ? 1 : grid, kDecodeThreads, cb_bytes, st>>>(
-        (const CodeT *)codes, (const LT *)l, lbub, norms_f32, user_stride, n_users, n_chunks, codebook, K,
+        (const CodeT *)codes, (const LT *)l, lbub, norms_f32, uoff, n_users, n_chunks, codebook, K,
         seg_start, n_seg, s, n_bit, mean, accumulate, out);
     GQ_LAUNCH_CHECK("hsq_decode_reduce_warp");
     return GQ_OK;
@@ -418,9 +418,9 @@ static int launch_decode_warp(const void *codes, const void *l, const float *lbu
 
 template <int D, typename CodeT, typename LT>
 static int launch_decode_d(const void *codes, const void *l, const float *lbub, const float *norms_f32,
-                           int64_t user_stride, int n_users, int64_t n_chunks, const float *codebook,
-                           int K, const int64_t *seg_start, int n_seg, int n_bit, int mean,
-                           int accumulate, float *out, cudaStream_t st)
+                           int64_t user_stride, const int64_t *user_offsets, int n_users, int64_t n_chunks,
+                           const float *codebook, int K, const int64_t *seg_start, int n_seg, int n_bit,
+                           int mean, int accumulate, float *out, cudaStream_t st)
 {
     const float s = (n_bit == 32) ? 1.0f : (float)(1u << n_bit);
     const size_t cb_bytes = (size_t)K * D * 4;
@@ -430,12 +430,19 @@ static int launch_decode_d(const void *codes, const void *l, const float *lbub, 
     constexpr bool kWarpPath = ((D4c & (D4c - 1)) == 0) && D4c <= 4;   // D = 4, 8, 16
     constexpr int DW = kWarpPath ? D : 16;
     if (kWarpPath && cb_bytes <= 64 * 1024 && n_users <= 8) {
-#define GQ_W(MU) return launch_decode_warp<DW, MU, CodeT, LT>(codes, l, lbub, norms_f32, user_stride, n_users, n_chunks, codebook, K, seg_start, n_seg, s, n_bit, mean, accumulate, out, st)
+        UserOffsets uoff;
+        for (int u = 0; u < 8; ++u)
+            uoff.off[u] = (u < n_users) ? (user_offsets ? user_offsets[u] : (int64_t)u * user_stride) : 0;
+#define GQ_W(MU) return launch_decode_warp<DW, MU, CodeT, LT>(codes, l, lbub, norms_f32, uoff, n_users, n_chunks, codebook, K, seg_start, n_seg, s, n_bit, mean, accumulate, out, st)
         if (n_users == 1) GQ_W(1);
         if (n_users == 2) GQ_W(2);
         if (n_users <= 4) GQ_W(4);
         GQ_W(8);
 #undef GQ_W
+    }
+    if (user_offsets != nullptr) {
+        set_error("scattered user records need chunk dim 4/8/16, a codebook <= 64 KB and <= 8 users");
+        return GQ_ERR_UNSUPPORTED;
     } else if (cb_bytes <= 64 * 1024) {
         auto kern = hsq_decode_reduce_kernel<D, CodeT, LT, true>;
         GQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cb_bytes));
@@ -461,15 +468,19 @@ static int launch_decode_d(const void *codes, const void *l, const float *lbub, 
 
 template <typename CodeT, typename LT>
 static int launch_decode(const void *codes, const void *l, const float *lbub, const float *norms_f32,
-                         int64_t user_stride, int n_users, int64_t n_chunks, int d,
+                         int64_t user_stride, const int64_t *user_offsets, int n_users, int64_t n_chunks, int d,
                          const float *codebook, int K, const int64_t *seg_start, int n_seg, int n_bit,
                          int mean, int accumulate, float *out, cudaStream_t st)
 {
     switch (d) {
-#define GQ_CASE(DD) case DD: return launch_decode_d<DD, CodeT, LT>(codes, l, lbub, norms_f32, user_stride, n_users, n_chunks, codebook, K, seg_start, n_seg, n_bit, mean, accumulate, out, st);
+#define GQ_CASE(DD) case DD: return launch_decode_d<DD, CodeT, LT>(codes, l, lbub, norms_f32, user_stride, user_offsets, n_users, n_chunks, codebook, K, seg_start, n_seg, n_bit, mean, accumulate, out, st);
         GQ_CASE(4) GQ_CASE(8) GQ_CASE(12) GQ_CASE(16) GQ_CASE(24) GQ_CASE(32) GQ_CASE(48) GQ_CASE(64)
 #undef GQ_CASE
         default: break;
+    }
+    if (user_offsets != nullptr) {
+        set_error("scattered user records are not supported for chunk dim %d", d);
+        return GQ_ERR_UNSUPPORTED;
     }
     const float s = (n_bit == 32) ? 1.0f : (float)(1u << n_bit);
     hsq_decode_reduce_generic_kernel<CodeT, LT><<<grid_for(n_chunks * (int64_t)d, 256), 256, 0, st>>>(
@@ -480,12 +491,13 @@ static int launch_decode(const void *codes, const void *l, const float *lbub, co
 }
 
 int hsq_decode_reduce(const void *codes, int code_bytes, const void *l, int l_bytes, const float *lbub,
-                      const float *norms_f32, int64_t user_stride, int n_users, int64_t n_chunks, int d,
+                      const float *norms_f32, int64_t user_stride, const int64_t *user_offsets, int n_users,
+                      int64_t n_chunks, int d,
                       const float *codebook, int K, const int64_t *seg_start, int n_seg, int n_bit,
                       int mean, int accumulate, float *out, cudaStream_t st)
 {
     if (n_chunks == 0) return GQ_OK;
-#define GQ_GO(CT, LTT) return launch_decode<CT, LTT>(codes, l, lbub, norms_f32, user_stride, n_users, n_chunks, d, codebook, K, seg_start, n_seg, n_bit, mean, accumulate, out, st)
+#define GQ_GO(CT, LTT) return launch_decode<CT, LTT>(codes, l, lbub, norms_f32, user_stride, user_offsets, n_users, n_chunks, d, codebook, K, seg_start, n_seg, n_bit, mean, accumulate, out, st)
     if (code_bytes == 1 && l_bytes == 1) GQ_GO(uint8_t, uint8_t);
     if (code_bytes == 1 && l_bytes == 4) GQ_GO(uint8_t, int32_t);
     if (code_bytes == 4 && l_bytes == 1) GQ_GO(int32_t, uint8_t);
@@ -509,10 +521,37 @@ f32_reduce_users_kernel(const float *__restrict__ in, int64_t user_stride, int n
     }
 }
 
-int launch_f32_reduce_users(const float *in, int64_t user_stride, int n_users, int64_t n, int mean,
-                            int accumulate, float *out, cudaStream_t st)
+__global__ void __launch_bounds__(256)
+f32_reduce_users_scattered_kernel(const float *__restrict__ in, const UserOffsets uoff, int n_users, int64_t n,
+                                  int mean, int accumulate, float *__restrict__ out)
+{
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        float acc = 0.0f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (u < n_users) {
+                const float x = *reinterpret_cast<const float *>(reinterpret_cast<const char *>(in) + uoff.off[u] + 4 * i);
+                acc = (u == 0) ? x : __fadd_rn(acc, x);
+            }
+        }
+        if (mean) acc = __fdiv_rn(acc, (float)n_users);
+        if (accumulate) acc = __fadd_rn(out[i], acc);
+        out[i] = acc;
+    }
+}
+
+int launch_f32_reduce_users(const float *in, int64_t user_stride, const int64_t *user_offsets, int n_users,
+                            int64_t n, int mean, int accumulate, float *out, cudaStream_t st)
 {
     if (n == 0) return GQ_OK;
+    if (user_offsets != nullptr) {
+        GQ_REQUIRE(n_users <= 8, "scattered user records support at most 8 users");
+        UserOffsets uoff;
+        for (int u = 0; u < 8; ++u) uoff.off[u] = (u < n_users) ? user_offsets[u] : 0;
+        f32_reduce_users_scattered_kernel<<<grid_for(n, 256), 256, 0, st>>>(in, uoff, n_users, n, mean, accumulate, out);
+        GQ_LAUNCH_CHECK("f32_reduce_users_scattered");
+        return GQ_OK;
+    }
     f32_reduce_users_kernel<<<grid_for(n, 256), 256, 0, st>>>(in, user_stride, n_users, n, mean,
                                                               accumulate, out);
     GQ_LAUNCH_CHECK("f32_reduce_users");

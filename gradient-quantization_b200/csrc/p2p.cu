@@ -1,0 +1,91 @@
+// p2p.cu -- peer-to-peer exchange of packed records over NVLink without a collective call.
+//
+// ps topology with one user per GPU: every rank encodes into a record buffer that its peers can
+// read directly (CUDA IPC mapping of peer device memory), a tiny barrier kernel tells the peers
+// "my record of step e is complete" with system-scope release stores into their flag arrays and
+// waits for theirs, and the fused decode-and-average kernel then pulls the 2/d bytes per element
+// of the other users straight out of peer HBM while it works.  Replaces the NCCL all-gather of
+// quantizers/ps_quantizer.py's exchange step (3 MB per rank: latency-, not bandwidth-bound).
+#include "gq_internal.cuh"
+
+using namespace gq;
+
+namespace gq {
+
+struct PeerFlags {
+    uint32_t *p[8];
+};
+
+// flags layout on every rank: uint32 flags[8]; flags[r] = last epoch rank r has announced to me
+__global__ void peer_barrier_kernel(uint32_t *local_flags, const PeerFlags peers, int rank, int n_ranks,
+                                    uint32_t epoch)
+{
+    const int u = threadIdx.x;
+    if (u < n_ranks) {
+        // everything this GPU wrote before the kernel (its packed record) becomes visible to peer u
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peers.p[u] + rank), "r"(epoch) : "memory");
+        uint32_t seen, spins = 0;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(local_flags + u) : "memory");
+            if ((int32_t)(seen - epoch) >= 0) break;
+            __nanosleep(100);
+        } while (++spins < (1u << 26));
+        if ((int32_t)(seen - epoch) < 0) __trap();   // a peer never arrived: fail loudly, do not hang
+    }
+}
+
+}  // namespace gq
+
+extern "C" {
+
+// cudaMalloc'ed, zero-initialised buffer whose IPC handle (64 bytes) can be shipped to the other
+// ranks of the node (e.g. with torch.distributed.all_gather_object).  Synchronous.
+int gq_ipc_alloc(size_t bytes, void **dev_ptr, void *handle_out_64)
+{
+    GQ_REQUIRE(bytes > 0 && dev_ptr && handle_out_64, "bad arguments");
+    GQ_CUDA(cudaMalloc(dev_ptr, bytes));
+    GQ_CUDA(cudaMemset(*dev_ptr, 0, bytes));
+    cudaIpcMemHandle_t h;
+    GQ_CUDA(cudaIpcGetMemHandle(&h, *dev_ptr));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(handle_out_64, &h, 64);
+    GQ_CUDA(cudaDeviceSynchronize());
+    return GQ_OK;
+}
+
+int gq_ipc_free(void *dev_ptr)
+{
+    if (dev_ptr) GQ_CUDA(cudaFree(dev_ptr));
+    return GQ_OK;
+}
+
+// Map a peer's buffer into this process (peer access is enabled lazily by the driver).
+int gq_ipc_open(const void *handle_64, void **peer_ptr)
+{
+    GQ_REQUIRE(handle_64 && peer_ptr, "bad arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle_64, 64);
+    GQ_CUDA(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return GQ_OK;
+}
+
+int gq_ipc_close(void *peer_ptr)
+{
+    if (peer_ptr) GQ_CUDA(cudaIpcCloseMemHandle(peer_ptr));
+    return GQ_OK;
+}
+
+// Cross-GPU barrier on `stream`: announce `epoch` to every rank's flag array and wait until every
+// rank has announced it here.  flag_ptrs[r] (host array) = address of rank r's flag array as
+// mapped in THIS process (flag_ptrs[rank] is the local one).  Epochs must increase by one per call.
+int gq_peer_barrier(void *const *flag_ptrs, int rank, int n_ranks, uint32_t epoch, gq_stream_t stream)
+{
+    GQ_REQUIRE(flag_ptrs && n_ranks >= 1 && n_ranks <= 8 && rank >= 0 && rank < n_ranks, "bad arguments");
+    PeerFlags pf;
+    for (int r = 0; r < 8; ++r) pf.p[r] = (r < n_ranks) ? reinterpret_cast<uint32_t *>(flag_ptrs[r]) : nullptr;
+    peer_barrier_kernel<<<1, 32, 0, as_stream(stream)>>>(pf.p[rank], pf, rank, n_ranks, epoch);
+    GQ_LAUNCH_CHECK("peer_barrier");
+    return GQ_OK;
+}
+
+}  // extern "C"

@@ -309,15 +309,40 @@ class FusedPlan:
                         src[g.arena_off:g.arena_off + g.n])
 
     # --------------------------------------------------------------- decode ---
-    def decode(self, first_user=0, n_users=None, mean=True, accumulate=False, out=None):
-        """out (arena layout) = [out +] reduce over records[first_user : first_user+n_users]."""
+    def supports_scattered(self):
+        """Peer-to-peer decode handles HSQ groups with chunk dim 4/8/16, a codebook of at most
+        64 KB and quantized norms, plus the identity tensors."""
+        for g in self.groups:
+            if g.kind == "identity":
+                continue
+            if g.kind != "hsq" or g.dim not in (4, 8, 16) or g.K * g.dim * 4 > 65536 or g.n_bit == 32:
+                return False
+        return True
+
+    def decode(self, first_user=0, n_users=None, mean=True, accumulate=False, out=None,
+               base_ptr=None, user_offsets=None):
+        """out (arena layout) = [out +] reduce over records[first_user : first_user+n_users].
+        base_ptr / user_offsets (ctypes int64 array): user 0's record address and every user's byte
+        offset from it, for records that live in different buffers (peer-to-peer exchange)."""
         out = self.arena if out is None else out
         n_users = self.n_users if n_users is None else n_users
         st = _lib.stream()
-        base = self.records.data_ptr() + first_user * self.record_bytes
-        stride = self.record_bytes
         mean = 1 if mean else 0
         acc = 1 if accumulate else 0
+        if user_offsets is not None:
+            for g in self.groups:
+                op = out.data_ptr() + g.arena_off * 4
+                if g.kind == "hsq":
+                    _lib.call("gq_hsq_decode_reduce_scattered", base_ptr + g.codes_off, g.code_bytes,
+                              base_ptr + g.l_off, g.l_bytes, base_ptr + g.lbub_off, user_offsets, n_users,
+                              g.n_chunks, g.dim, _lib.ptr(g.codebook), g.K, _lib.ptr(g.seg_start), g.n_seg,
+                              g.n_bit, mean, acc, op, st)
+                else:
+                    _lib.call("gq_f32_reduce_users_scattered", base_ptr + g.raw_off, user_offsets, n_users, g.n,
+                              mean, acc, op, st)
+            return out
+        base = self.records.data_ptr() + first_user * self.record_bytes
+        stride = self.record_bytes
         for g in self.groups:
             op = out.data_ptr() + g.arena_off * 4
             if g.kind == "hsq":

@@ -28,6 +28,32 @@ class PSQuantizer(QuantizerBase):
                 param.server_error = torch.zeros_like(param)
         if self.plan is not None and self.two_phase:
             self._phase2_plan = None  # built lazily (a 1-user plan for the averaged gradient)
+        self.p2p = None
+        if self.distributed and self.plan is not None:
+            self._setup_p2p()
+
+    def _setup_p2p(self):
+        """Peer-to-peer exchange instead of an NCCL all-gather when every rank can do it
+        (args.p2p = False or GQ_P2P=0 turns it off)."""
+        import os
+        import torch.distributed as dist
+        want = getattr(self.args, "p2p", True) and os.environ.get("GQ_P2P", "1") != "0"
+        ok = 1 if (want and self.world <= 8 and self.plan.supports_scattered()) else 0
+        p2p = None
+        if ok:
+            try:
+                from .p2p import PeerRecords
+                p2p = PeerRecords(self.plan.record_bytes, self.rank, self.world, self.device)
+            except Exception as e:  # noqa: BLE001
+                print("gq_b200: peer-to-peer exchange unavailable (%s); using NCCL all-gather" % (e,))
+                ok = 0
+        flag = torch.tensor([ok], device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 1:
+            self.p2p = p2p
+            self.plan.records = p2p.records          # [2, record_bytes]: row = step parity
+        elif p2p is not None:
+            p2p.close()
 
     # ------------------------------------------------------------------ record
     def record(self, user, epoch, uniforms=None):
@@ -38,6 +64,7 @@ class PSQuantizer(QuantizerBase):
         if self.distributed and user != self.rank:
             raise _lib.GQError("distributed mode: rank %d records user %d only" % (self.rank, self.rank))
         plan.gather(self._grads())
+        slot = self.p2p.parity if self.p2p is not None else user   # row of plan.records to write
         if self.error_feedback:
             err = self._ef_buffers(user)
             n = plan.arena.numel()
@@ -46,12 +73,12 @@ class PSQuantizer(QuantizerBase):
                       _lib.ptr(plan.arena), _lib.stream())
             for p, v in zip(self.parameters, plan.views()):
                 p.grad.data = v               # the reference mutates param.grad in place
-            plan.encode(user, uniforms=uniforms)
+            plan.encode(slot, uniforms=uniforms)
             # error[user] = grad - decompress(compress(grad))   (:36-39)
-            dec = plan.decode(first_user=user, n_users=1, mean=False, out=self._scratch())
+            dec = plan.decode(first_user=slot, n_users=1, mean=False, out=self._scratch())
             _lib.call("gq_sub", _lib.ptr(plan.arena), _lib.ptr(dec), n, _lib.ptr(err), _lib.stream())
         else:
-            plan.encode(user, uniforms=uniforms)
+            plan.encode(slot, uniforms=uniforms)
 
     def _scratch(self):
         if not hasattr(self, "_scratch_buf"):
@@ -70,6 +97,29 @@ class PSQuantizer(QuantizerBase):
                     self.compressors[i].compress(param.grad.data))
             self.compressed_gradients[i].append(decompressed_g)
 
+    # ----------------------------------------------- fused building blocks
+    def encode_local(self, user, src=None, uniforms=None):
+        """Pack one user's gradient (the arena, or `src` laid out like it) into its record.
+        Returns the row of plan.records that was written."""
+        slot = self.p2p.parity if self.p2p is not None else user
+        self.plan.encode(slot, src=src, uniforms=uniforms)
+        return slot
+
+    def exchange_and_decode(self, out=None):
+        """Make every user's record available and decode-and-average them into `out`
+        (default: the arena).  Peer-to-peer: one barrier kernel, the decode kernel reads the
+        peers' records over NVLink.  Otherwise: NCCL all-gather (or nothing in one process)."""
+        plan = self.plan
+        out = plan.arena if out is None else out
+        if self.p2p is not None:
+            self.p2p.barrier()
+            g = plan.decode(n_users=self.world, mean=True, out=out, base_ptr=self.p2p.user0_record_ptr(),
+                            user_offsets=self.p2p.user_offsets())
+            self.p2p.advance()
+            return g
+        self.exchange()
+        return plan.decode(mean=True, out=out)
+
     # ------------------------------------------------------------------- apply
     def exchange(self):
         """All-gather the packed records: rank r's record is already in slot r."""
@@ -79,9 +129,7 @@ class PSQuantizer(QuantizerBase):
     def apply(self, uniforms=None):
         if self.plan is None:
             return self._apply_per_parameter()
-        plan = self.plan
-        self.exchange()
-        g = plan.decode(mean=True, out=plan.arena)
+        g = self.exchange_and_decode()
         if self.two_phase:
             g = self._second_phase(g, uniforms)
         self._set_grads_from(g)

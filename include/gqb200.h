@@ -135,6 +135,19 @@ int gq_hsq_decode_reduce(const void *codes, int code_bytes, const void *l, int l
                          const int64_t *seg_start, int n_seg, int n_bit,
                          int mean, int accumulate, float *out, gq_stream_t stream);
 
+/* Same reduction, but user u's arrays are found at (pointer of user 0) + user_byte_offsets[u]
+ * (host array, n_users <= 8, offsets may be any 64-bit distance): the packed records need not be
+ * equally spaced -- with peer-to-peer exchange each user's record lives in another GPU's memory
+ * (mapped with gq_ipc_open) and is read over NVLink by the decode kernel itself.
+ * Chunk dims 4, 8, 16 with a codebook of at most 64 KB; quantized norms only. */
+int gq_hsq_decode_reduce_scattered(const void *codes, int code_bytes, const void *l, int l_bytes,
+                                   const float *lbub, const int64_t *user_byte_offsets, int n_users,
+                                   int64_t n_chunks, int d, const float *codebook, int K,
+                                   const int64_t *seg_start, int n_seg, int n_bit, int mean, int accumulate,
+                                   float *out, gq_stream_t stream);
+int gq_f32_reduce_users_scattered(const float *in, const int64_t *user_byte_offsets, int n_users, int64_t n,
+                                  int mean, int accumulate, float *out, gq_stream_t stream);
+
 /* out[i] = (sum_u in[u*user_stride_bytes + 4*i]) / U (mean) -- identity tensors
  * (compressors/identical_compressor.py:5-11 under ps_quantizer.py:48). */
 int gq_f32_reduce_users(const float *in, int64_t user_stride_bytes, int n_users, int64_t n,
@@ -212,6 +225,22 @@ int gq_pvc_search(const float *grad, int64_t n_chunks, int d, const float *dagge
 int gq_hsq_tc_debug(const float *grad, int64_t n_chunks, const float *codebook, void *codes,
                     float *u_out, const int64_t *seg_start, int n_seg, float *dbg_scores,
                     int dbg_tiles, gq_stream_t stream);
+
+/* ------------------------------------------------------------------------- */
+/* Peer-to-peer exchange of packed records (one user per GPU on one NVLink/NVSwitch node).
+ * Replaces the exchange step of PSQuantizer (quantizers/ps_quantizer.py:44-48, a Python list
+ * append in the reference; an NCCL all-gather in the plain distributed path).
+ * gq_ipc_alloc: cudaMalloc + zero a buffer and return its 64-byte CUDA IPC handle (ship it to the
+ *   other ranks, e.g. torch.distributed.all_gather_object).  gq_ipc_open maps a peer's buffer.
+ * gq_peer_barrier: on `stream`, announce `epoch` in every rank's flag array (system-scope release
+ *   store) and wait until every rank announced it here.  flag_ptrs is a HOST array of n_ranks
+ *   device addresses (uint32[8] each; flag_ptrs[rank] is the local array), epochs increase by 1.
+ *   Traps (sticky CUDA error) instead of hanging if a peer never arrives. */
+int gq_ipc_alloc(size_t bytes, void **dev_ptr, void *handle_out_64);
+int gq_ipc_free(void *dev_ptr);
+int gq_ipc_open(const void *handle_64, void **peer_ptr);
+int gq_ipc_close(void *peer_ptr);
+int gq_peer_barrier(void *const *flag_ptrs, int rank, int n_ranks, uint32_t epoch, gq_stream_t stream);
 
 /* ------------------------------------------------------------------------- */
 /* Elementwise helpers the quantizers need around the codecs.
