@@ -399,17 +399,15 @@ def main():
     for p, v in zip(params, plan.views()):
         p.grad = v
 
-    # keep the same loop running until the sampler has seen the clocks under load
-    t_end = time.time() + 0.6
-    i = 0
-    while time.time() < t_end or len(sampler.samples) < 5:
+    # keep the same loop running (~0.6 s) so that the sampler sees the clocks under load; the number
+    # of extra steps is derived from the all-reduced step time, hence identical on every rank
+    # (the steps contain collectives / peer barriers)
+    n_extra = int(min(max(0.6 / (ms_per_step * 1e-3), 50), 20000))
+    for i in range(n_extra):
         step(i)
-        i += 1
-        if i % 50 == 0:
+        if i % 200 == 199:
             torch.cuda.synchronize()
-        if time.time() > t_end + 3:
-            break
-    torch.cuda.synchronize()
+    barrier()
     clocks = sampler.finish()
 
     if rank != 0:
