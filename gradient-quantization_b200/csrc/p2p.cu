@@ -6,6 +6,8 @@
 // waits for theirs, and the fused decode-and-average kernel then pulls the 2/d bytes per element
 // of the other users straight out of peer HBM while it works.  Replaces the NCCL all-gather of
 // quantizers/ps_quantizer.py's exchange step (3 MB per rank: latency-, not bandwidth-bound).
+#include <string.h>
+
 #include "gq_internal.cuh"
 
 using namespace gq;
@@ -32,6 +34,28 @@ __global__ void peer_barrier_kernel(uint32_t *local_flags, const PeerFlags peers
         } while (++spins < (1u << 26));
         if ((int32_t)(seen - epoch) < 0) __trap();   // a peer never arrived: fail loudly, do not hang
     }
+}
+
+struct PeerPtrs {
+    const uint4 *p[8];
+};
+
+// pull every user's packed record out of its owner's memory into the local [U, stride] buffer:
+// wide (16-byte) loads, many in flight per thread, so NVLink latency is covered by parallelism
+__global__ void __launch_bounds__(256)
+peer_gather_kernel(uint4 *__restrict__ dst, const PeerPtrs src, size_t n16, size_t dst_stride16)
+{
+    const int u = blockIdx.y;
+    const uint4 *s = src.p[u];
+    uint4 *d = dst + (size_t)u * dst_stride16;
+    const size_t step = (size_t)gridDim.x * 256;
+    size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    for (; i + 3 * step < n16; i += 4 * step) {
+        const uint4 a = __ldcv(s + i), b = __ldcv(s + i + step), c = __ldcv(s + i + 2 * step),
+                    e = __ldcv(s + i + 3 * step);
+        d[i] = a; d[i + step] = b; d[i + 2 * step] = c; d[i + 3 * step] = e;
+    }
+    for (; i < n16; i += step) d[i] = __ldcv(s + i);
 }
 
 }  // namespace gq
@@ -85,6 +109,26 @@ int gq_peer_barrier(void *const *flag_ptrs, int rank, int n_ranks, uint32_t epoc
     for (int r = 0; r < 8; ++r) pf.p[r] = (r < n_ranks) ? reinterpret_cast<uint32_t *>(flag_ptrs[r]) : nullptr;
     peer_barrier_kernel<<<1, 32, 0, as_stream(stream)>>>(pf.p[rank], pf, rank, n_ranks, epoch);
     GQ_LAUNCH_CHECK("peer_barrier");
+    return GQ_OK;
+}
+
+// After gq_peer_barrier: copy n_ranks records of `bytes` each (a multiple of 16) from
+// src_ptrs[r] (host array of device addresses, peer-mapped or local) to dst + r * dst_stride.
+int gq_peer_gather(void *dst, void *const *src_ptrs, size_t bytes, size_t dst_stride, int n_ranks,
+                   gq_stream_t stream)
+{
+    GQ_REQUIRE(dst && src_ptrs && n_ranks >= 1 && n_ranks <= 8, "bad arguments");
+    GQ_REQUIRE(bytes % 16 == 0 && dst_stride % 16 == 0 && ((uintptr_t)dst & 15) == 0, "16-byte granularity");
+    PeerPtrs pp;
+    for (int r = 0; r < 8; ++r) pp.p[r] = (r < n_ranks) ? reinterpret_cast<const uint4 *>(src_ptrs[r]) : nullptr;
+    const size_t n16 = bytes / 16;
+    int bx = (int)((n16 + 1023) / 1024);
+    const int cap = sm_count() * 4 / n_ranks + 1;
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    peer_gather_kernel<<<dim3(bx, n_ranks), 256, 0, as_stream(stream)>>>(reinterpret_cast<uint4 *>(dst), pp, n16,
+                                                                          dst_stride / 16);
+    GQ_LAUNCH_CHECK("peer_gather");
     return GQ_OK;
 }
 

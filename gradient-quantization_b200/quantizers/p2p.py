@@ -63,6 +63,12 @@ class PeerRecords:
         _lib.call("gq_peer_barrier", ctypes.cast(self._flag_ptrs, ctypes.c_void_p), self.rank, self.world,
                   self.epoch, _lib.stream())
 
+    def gather(self, dst):
+        """Pull every user's record of the current parity into dst ([U, record_bytes], local)."""
+        srcs = (ctypes.c_void_p * self.world)(*[b + self.parity * self.record_bytes for b in self.base])
+        _lib.call("gq_peer_gather", dst.data_ptr(), ctypes.cast(srcs, ctypes.c_void_p), self.record_bytes,
+                  dst.stride(0), self.world, _lib.stream())
+
     def user0_record_ptr(self):
         return self.base[0] + self.parity * self.record_bytes
 

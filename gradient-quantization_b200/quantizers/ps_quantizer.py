@@ -51,6 +51,11 @@ class PSQuantizer(QuantizerBase):
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if int(flag.item()) == 1:
             self.p2p = p2p
+            # "gather" (default): pull the peers' records into the local [U, record_bytes] buffer with
+            # a wide-load copy kernel, then decode locally.  "direct": the decode kernel reads the
+            # peers' records itself (fewer bytes moved twice, but latency-bound byte loads over NVLink).
+            self.p2p_mode = os.environ.get("GQ_P2P_MODE", getattr(self.args, "p2p_mode", "gather"))
+            self._gathered = self.plan.records       # [U, record_bytes], local
             self.plan.records = p2p.records          # [2, record_bytes]: row = step parity
         elif p2p is not None:
             p2p.close()
@@ -113,8 +118,17 @@ class PSQuantizer(QuantizerBase):
         out = plan.arena if out is None else out
         if self.p2p is not None:
             self.p2p.barrier()
-            g = plan.decode(n_users=self.world, mean=True, out=out, base_ptr=self.p2p.user0_record_ptr(),
-                            user_offsets=self.p2p.user_offsets())
+            if self.p2p_mode == "direct":
+                g = plan.decode(n_users=self.world, mean=True, out=out, base_ptr=self.p2p.user0_record_ptr(),
+                                user_offsets=self.p2p.user_offsets())
+            else:
+                self.p2p.gather(self._gathered)
+                own = plan.records
+                plan.records = self._gathered
+                try:
+                    g = plan.decode(n_users=self.world, mean=True, out=out)
+                finally:
+                    plan.records = own
             self.p2p.advance()
             return g
         self.exchange()

@@ -241,6 +241,10 @@ int gq_ipc_free(void *dev_ptr);
 int gq_ipc_open(const void *handle_64, void **peer_ptr);
 int gq_ipc_close(void *peer_ptr);
 int gq_peer_barrier(void *const *flag_ptrs, int rank, int n_ranks, uint32_t epoch, gq_stream_t stream);
+/* After the barrier: pull n_ranks records of `bytes` each (multiple of 16) from src_ptrs[r] (HOST
+ * array of device addresses, peer-mapped or local) into dst + r*dst_stride with wide loads. */
+int gq_peer_gather(void *dst, void *const *src_ptrs, size_t bytes, size_t dst_stride, int n_ranks,
+                   gq_stream_t stream);
 
 /* ------------------------------------------------------------------------- */
 /* Elementwise helpers the quantizers need around the codecs.
