@@ -204,6 +204,12 @@ hsq_search_tc_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    // debug builds: CTA 0 time-stamps pipeline events, trace[event * 128 + it] (events: 0 TMA issued,
+    // 1 MMA issued, 2 accumulators seen by the epilogue, 3 TMEM released, 4 stage released, 5 tile done)
+    long long *trace = nullptr;
+    if (kDebug && dbg_scores != nullptr && blockIdx.x == 0)
+        trace = reinterpret_cast<long long *>(dbg_scores + (size_t)dbg_tiles * kTileM * kK + n_chunks * 24);
+#define GQ_TRACE(ev, it_) do { if (kDebug && trace != nullptr && (it_) < 128) trace[(ev) * 128 + (it_)] = clock64(); } while (0)
     // every CTA owns a contiguous range of tiles (balanced to within one tile)
     const int64_t n_tiles = (n_chunks + kTileM - 1) / kTileM;
     const int64_t tq = n_tiles / gridDim.x, trem = n_tiles % gridDim.x;
@@ -249,6 +255,7 @@ hsq_search_tc_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_
                 mbar_wait(bar_empty + 8 * s, ((it / kStages) & 1) ^ 1, flags & 1);
                 mbar_expect_tx(bar_full + 8 * s, kTileBytes);
                 tma_load_2d(smem_u32(s_a + s * kTileBytes), &map_grad, bar_full + 8 * s, 0, (int)(tile * kTileM));
+                GQ_TRACE(0, it);
             }
         }
     } else if (warp == 1) {
@@ -268,6 +275,7 @@ hsq_search_tc_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_
                 mma_tf32(taddr, adesc, bdesc, 0u);              // k = 0..7   (bytes  0..31 of each row)
                 mma_tf32(taddr, adesc + 2, bdesc + 2, 1u);      // k = 8..15  (bytes 32..63): +32 B = +2 units
                 mma_commit(bar_tfull + 8 * s);
+                GQ_TRACE(1, it);
             }
         }
     } else if (warp >= 4) {
@@ -292,6 +300,7 @@ hsq_search_tc_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_
             mbar_wait(bar_tfull + 8 * s, (it / kStages) & 1, flags & 4);  // accumulators complete
             __syncwarp();                                      // converged before .sync.aligned TMEM loads
             tc_fence_after();
+            if (quad == 0 && lane == 0) GQ_TRACE(2, it);
 
             // pass over the 256 approximate scores of this row: max |.| per group of 4 codewords
             float gm[kNumGroups];
@@ -316,6 +325,7 @@ hsq_search_tc_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * s);
+            if (quad == 0 && lane == 0) GQ_TRACE(3, it);
 
             // this row's chunk, from the (swizzled) smem tile
             float v[kD];
@@ -339,6 +349,7 @@ hsq_search_tc_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_
             // overwrites the row under the read -- tests/tc_diag.py shows v[12..15] of tile it+6.
             const uint32_t all_loaded = __ballot_sync(0xffffffffu, !(n2 < 0.0f));   // always all ones
             if (lane == 0) mbar_arrive(bar_empty + 8 * s + ((all_loaded == 0u) ? 8u : 0u));
+            if (quad == 0 && lane == 0) GQ_TRACE(4, it);
 
             float amax = fmaxf(gm[0], gm[1]);
 #pragma unroll
@@ -409,6 +420,7 @@ hsq_search_tc_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_
                 const int seg = valid ? cached_segment(segc, seg_start, n_seg, c) : -1;
                 minmax_add_warp(mm, valid, seg, best_u, minmax_keys);
             }
+            if (quad == 0 && lane == 0) GQ_TRACE(5, it);
         }
         if (minmax_keys != nullptr) minmax_flush_warp(mm, minmax_keys);
     }
