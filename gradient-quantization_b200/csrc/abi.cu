@@ -39,6 +39,12 @@ int sm_count()
     return cached[dev];
 }
 
+bool pdl_enabled()
+{
+    static const bool on = [] { const char *f = getenv("GQ_PDL"); return !(f && atoi(f) == 0); }();
+    return on;
+}
+
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 }  // namespace gq

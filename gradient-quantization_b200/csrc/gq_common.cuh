@@ -35,6 +35,33 @@ int sm_count();
 
 static inline cudaStream_t as_stream(gq_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// ------------------------------------------- programmatic dependent launch ---
+// The kernels of one encode/decode step are short (2-80 us) and strictly chained, so launch
+// latency and prologues (codebook staging, TMEM allocation) are a visible fraction of the step.
+// Every kernel of the chain calls pdl_launch_dependents() first (the next kernel's grid may be
+// scheduled as soon as SMs free up) and pdl_wait() before it touches anything a predecessor
+// wrote; launches go through launch_pdl().  GQ_PDL=0 in the environment turns the attribute off.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 // ---------------------------------------------------- ordered float keys ---
 // Monotone map fp32 -> uint32 so that unsigned atomicMin/atomicMax implement
 // float min/max (used for the per-tensor lb/ub of the norm quantizer).

@@ -166,6 +166,8 @@ hsq_search_generic_kernel(const float *__restrict__ grad, int64_t n_chunks, int 
 
 __global__ void minmax_init_kernel(uint32_t *keys, int n_seg, uint32_t *barrier)
 {
+    pdl_launch_dependents();
+    pdl_wait();   // the keys may still be read by the previous step's quantize kernel
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0 && barrier != nullptr) *barrier = 0u;
     if (i < n_seg) {
@@ -176,8 +178,7 @@ __global__ void minmax_init_kernel(uint32_t *keys, int n_seg, uint32_t *barrier)
 
 int launch_minmax_init(uint32_t *keys, int n_seg, cudaStream_t st, uint32_t *barrier)
 {
-    minmax_init_kernel<<<(n_seg + 127) / 128, 128, 0, st>>>(keys, n_seg, barrier);
-    GQ_LAUNCH_CHECK("minmax_init");
+    GQ_CUDA(launch_pdl(minmax_init_kernel, dim3((n_seg + 127) / 128), dim3(128), 0, st, keys, n_seg, barrier));
     return GQ_OK;
 }
 

@@ -56,6 +56,92 @@ norm_quantize_kernel(const float *__restrict__ u, int64_t n, const int64_t *__re
                               n_seg, s, random, uniforms, seed, offset, l, keys);
 }
 
+// Same, with the segment table and the decoded lb/ub staged in shared memory: the kernel is a
+// single wave whose run time is one chain of dependent loads per thread, and the 7-step binary
+// search over global memory was the longest link of that chain.
+constexpr int kQuantMaxSeg = 1024;
+template <typename LT>
+__global__ void __launch_bounds__(256)
+norm_quantize_smem_kernel(const float *__restrict__ u, int64_t n, const int64_t *__restrict__ seg_start,
+                          int n_seg, float s, int random, const float *__restrict__ uniforms,
+                          uint64_t seed, uint64_t offset, LT *__restrict__ l, float *__restrict__ lbub,
+                          const uint32_t *__restrict__ keys)
+{
+    extern __shared__ int64_t s_seg[];                                   // [n_seg + 1]
+    float *s_lbub = reinterpret_cast<float *>(s_seg + n_seg + 1);       // [2 * n_seg]
+    pdl_launch_dependents();
+    for (int i = threadIdx.x; i <= n_seg; i += 256) s_seg[i] = seg_start[i];
+    pdl_wait();   // keys and u come from the search kernel
+    for (int i = threadIdx.x; i < 2 * n_seg; i += 256) {
+        const float f = key_to_float(keys[i]);
+        s_lbub[i] = f;
+        if (blockIdx.x == 0) lbub[i] = f;
+    }
+    const int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int64_t n4 = (n + 3) / 4;
+    // prefetch this thread's data while the tables land
+    float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), rv = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool in = q < n4;
+    const bool full = in && (q * 4 + 3 < n);
+    if (full) {
+        xv = __ldg(reinterpret_cast<const float4 *>(u) + q);
+        if (random && uniforms) rv = __ldg(reinterpret_cast<const float4 *>(uniforms) + q);
+    }
+    __syncthreads();
+    if (!in) return;
+    const int64_t i0 = q * 4;
+    float x[4] = {xv.x, xv.y, xv.z, xv.w}, r[4] = {rv.x, rv.y, rv.z, rv.w};
+    if (!full) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            x[t] = (i0 + t < n) ? u[i0 + t] : 0.0f;
+            r[t] = (random && uniforms && i0 + t < n) ? uniforms[i0 + t] : 0.0f;
+        }
+    }
+    if (random && !uniforms) {
+        if (((offset + (uint64_t)i0) & 3u) == 0) {
+            const uint4 w = philox4x32_10(seed, (offset + (uint64_t)i0) >> 2);
+            r[0] = u01(w.x); r[1] = u01(w.y); r[2] = u01(w.z); r[3] = u01(w.w);
+        } else {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) r[t] = philox_uniform(seed, offset, (uint64_t)(i0 + t));
+        }
+    }
+    // segment of the first chunk by binary search in shared memory, then walk forward
+    int seg = 0;
+    {
+        int lo = 0, hi = n_seg;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (s_seg[mid] <= i0) lo = mid; else hi = mid;
+        }
+        seg = lo;
+    }
+    int lv[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const int64_t i = i0 + t;
+        if (i < n) {
+            while (i >= s_seg[seg + 1]) ++seg;
+            lv[t] = psc_level(x[t], s_lbub[2 * seg], s_lbub[2 * seg + 1], s, random, r[t]);
+        } else {
+            lv[t] = 0;
+        }
+    }
+    if (full) {
+        if (sizeof(LT) == 1) {
+            reinterpret_cast<uint32_t *>(l)[q] =
+                (uint32_t)lv[0] | ((uint32_t)lv[1] << 8) | ((uint32_t)lv[2] << 16) | ((uint32_t)lv[3] << 24);
+        } else {
+            reinterpret_cast<int4 *>(l)[q] = make_int4(lv[0], lv[1], lv[2], lv[3]);
+        }
+    } else {
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+            if (i0 + t < n) l[i0 + t] = (LT)lv[t];
+    }
+}
+
 template <typename LT>
 __global__ void __launch_bounds__(256)
 norm_dequantize_kernel(const LT *__restrict__ l, int64_t n, const int64_t *__restrict__ seg_start,
@@ -92,7 +178,22 @@ int launch_norm_quantize(const float *u, int64_t n, const int64_t *seg_start, in
                          int l_bytes, float *lbub, const uint32_t *keys, cudaStream_t st)
 {
     const float s = (float)(1u << n_bit);
-    const int grid = grid_for(n > 0 ? (n + 3) / 4 : 1, 256);
+    const int64_t n4 = (n + 3) / 4;
+    const bool aligned = (((uintptr_t)u & 15) == 0) && (uniforms == nullptr || ((uintptr_t)uniforms & 15) == 0) &&
+                         (((uintptr_t)l & (4 * (size_t)l_bytes - 1)) == 0);
+    if (n_seg <= kQuantMaxSeg && aligned && n4 > 0 && n4 < ((int64_t)1 << 31) * 256) {
+        // one thread per four chunks, tables in shared memory
+        const size_t smem = (size_t)(n_seg + 1) * 8 + (size_t)n_seg * 8;
+        const unsigned grid = (unsigned)((n4 + 255) / 256);
+        if (l_bytes == 1)
+            GQ_CUDA(launch_pdl(norm_quantize_smem_kernel<uint8_t>, dim3(grid), dim3(256), smem, st, u, n, seg_start,
+                               n_seg, s, random, uniforms, seed, offset, (uint8_t *)l, lbub, keys));
+        else
+            GQ_CUDA(launch_pdl(norm_quantize_smem_kernel<int32_t>, dim3(grid), dim3(256), smem, st, u, n, seg_start,
+                               n_seg, s, random, uniforms, seed, offset, (int32_t *)l, lbub, keys));
+        return GQ_OK;
+    }
+    const int grid = grid_for(n > 0 ? n4 : 1, 256);
     if (l_bytes == 1)
         norm_quantize_kernel<uint8_t><<<grid, 256, 0, st>>>(u, n, seg_start, n_seg, s, random, uniforms,
                                                             seed, offset, (uint8_t *)l, lbub, keys);
@@ -300,8 +401,10 @@ hsq_decode_reduce_warp_kernel(const CodeT *__restrict__ codes, const LT *__restr
     constexpr int D4 = D / 4;
     static_assert((D4 & (D4 - 1)) == 0 && D4 <= 4, "D = 4, 8 or 16");
     const float4 *cb4g = reinterpret_cast<const float4 *>(codebook);
-    for (int i = threadIdx.x; i < K * D4; i += kDecodeThreads) s_cbd[i] = __ldg(cb4g + i);
+    pdl_launch_dependents();
+    for (int i = threadIdx.x; i < K * D4; i += kDecodeThreads) s_cbd[i] = __ldg(cb4g + i);   // static codebook
     __syncthreads();
+    pdl_wait();   // the packed records come from the encode kernels / the exchange
     const int lane = threadIdx.x & 31;
     constexpr int kWarps = kDecodeThreads / 32;
     const float inv_s = 1.0f / s;
@@ -409,10 +512,9 @@ static int launch_decode_warp(const void *codes, const void *l, const float *lbu
     const int64_t wblocks = (iters + kDecodeThreads / 32 - 1) / (kDecodeThreads / 32);
     int64_t cap = (int64_t)sm_count() * (occ < 1 ? 1 : occ);
     int grid = (int)(wblocks < cap ? wblocks : cap);
-    kern<<<grid < 1 ? 1 : grid, kDecodeThreads, cb_bytes, st>>>(
-        (const CodeT *)codes, (const LT *)l, lbub, norms_f32, uoff, n_users, n_chunks, codebook, K,
-        seg_start, n_seg, s, n_bit, mean, accumulate, out);
-    GQ_LAUNCH_CHECK("hsq_decode_reduce_warp");
+    GQ_CUDA(launch_pdl(kern, dim3(grid < 1 ? 1 : grid), dim3(kDecodeThreads), cb_bytes, st, (const CodeT *)codes,
+                       (const LT *)l, lbub, norms_f32, uoff, n_users, n_chunks, codebook, K, seg_start, n_seg, s,
+                       n_bit, mean, accumulate, out));
     return GQ_OK;
 }
 
@@ -510,6 +612,8 @@ __global__ void __launch_bounds__(256)
 f32_reduce_users_kernel(const float *__restrict__ in, int64_t user_stride, int n_users, int64_t n,
                         int mean, int accumulate, float *__restrict__ out)
 {
+    pdl_launch_dependents();
+    pdl_wait();
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
         float acc = in[i];
         for (int u = 1; u < n_users; ++u)
@@ -552,9 +656,8 @@ int launch_f32_reduce_users(const float *in, int64_t user_stride, const int64_t 
         GQ_LAUNCH_CHECK("f32_reduce_users_scattered");
         return GQ_OK;
     }
-    f32_reduce_users_kernel<<<grid_for(n, 256), 256, 0, st>>>(in, user_stride, n_users, n, mean,
-                                                              accumulate, out);
-    GQ_LAUNCH_CHECK("f32_reduce_users");
+    GQ_CUDA(launch_pdl(f32_reduce_users_kernel, dim3(grid_for(n, 256)), dim3(256), 0, st, in, user_stride, n_users,
+                       n, mean, accumulate, out));
     return GQ_OK;
 }
 

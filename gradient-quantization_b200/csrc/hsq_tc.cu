@@ -188,6 +188,7 @@ hsq_search_tc_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_
                      float *__restrict__ dbg_scores, int dbg_tiles, int flags, const TcTail tail)
 {
     constexpr int kThreads = 128 + 128 * kEpiGroups;
+    pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned, still a shared pointer
     uint8_t *s_a = smem + kOffA;
@@ -243,6 +244,10 @@ hsq_search_tc_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
+    // everything above (barrier init, codebook planes, TMEM allocation) reads only the static
+    // codebook and overlaps the tail of the previous kernel; the gradient, the min/max keys and
+    // the output buffers are touched only after this point
+    pdl_wait();
 
     if (warp == 0) {
         // ------------------------------------------------------ TMA producer ---
@@ -351,9 +356,16 @@ hsq_search_tc_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_
             if (lane == 0) mbar_arrive(bar_empty + 8 * s + ((all_loaded == 0u) ? 8u : 0u));
             if (quad == 0 && lane == 0) GQ_TRACE(4, it);
 
-            float amax = fmaxf(gm[0], gm[1]);
+            // row maximum as a tree (four independent chains, then a 4-way merge) rather than one
+            // 32-deep dependent chain
+            float am[4];
 #pragma unroll
-            for (int g = 2; g < kNumGroups; g += 2) amax = fmaxf(amax, fmaxf(gm[g], gm[g + 1]));
+            for (int q = 0; q < 4; ++q) {
+                am[q] = fmaxf(gm[16 * q], gm[16 * q + 1]);
+#pragma unroll
+                for (int g = 2; g < 16; g += 2) am[q] = fmaxf(am[q], fmaxf(gm[16 * q + g], gm[16 * q + g + 1]));
+            }
+            const float amax = fmaxf(fmaxf(am[0], am[1]), fmaxf(am[2], am[3]));
             const float thr = amax - kMargin * sqrtf(n2);
             // candidate groups: gm[g] >= thr.  d = gm - thr on the FMA pipe, sign bits funnelled
             // into two 32-bit words (bit g of below[g >> 5] set = group g is below the threshold).
@@ -544,9 +556,9 @@ static int launch_tc(const float *grad, int64_t n_chunks, const float *codebook,
     do {                                                                                                       \
         auto kern = tc::hsq_search_tc_kernel<G, DBG>;                                                          \
         GQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes)); \
-        kern<<<grid, 128 + 128 * G, tc::kSmemBytes, st>>>(mg, mc, codebook, n_chunks, (uint8_t *)codes, u_out, \
-                                                          seg_start, n_seg, minmax_keys, dbg_scores, dbg_tiles, \
-                                                          flags, tail);                                        \
+        GQ_CUDA(launch_pdl(kern, dim3(grid), dim3(128 + 128 * G), (size_t)tc::kSmemBytes, st, mg, mc, codebook,     \
+                           n_chunks, (uint8_t *)codes, u_out, seg_start, n_seg, minmax_keys, dbg_scores,        \
+                           dbg_tiles, flags, tail));                                                           \
     } while (0)
     if (dbg) {
         if (groups == 3) GQ_TC_LAUNCH(3, true); else GQ_TC_LAUNCH(2, true);

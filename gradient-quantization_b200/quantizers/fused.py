@@ -304,9 +304,8 @@ class FusedPlan:
                           _lib.ptr(g.k_prefix), g.n_seg, None, base + g.idx_off, base + g.val_off,
                           _lib.ptr(self.workspace), self.workspace.numel(), st)
             elif g.kind == "identity":
-                if g.n:
-                    rec[g.raw_off:g.raw_off + g.n * 4].view(torch.float32).copy_(
-                        src[g.arena_off:g.arena_off + g.n])
+                if g.n:   # out = a + 0 * b: a plain copy of the raw fp32 tensors into the record
+                    _lib.call("gq_f32_reduce_users", gp, 0, 1, g.n, 0, 0, base + g.raw_off, st)
 
     # --------------------------------------------------------------- decode ---
     def supports_scattered(self):
