@@ -77,6 +77,14 @@ def test_hsq_adversarial_ties_and_specials():
         rows.append(r)
     for _ in range(300):                                              # low-precision values: many exact ties
         rows.append((rs.randint(-2, 3, size=d)).astype(np.float32))
+    for sc in (1e-18, 1e-30, 1e-36, 3e-39, 1e-42):                    # down into the denormals, where the
+        for _ in range(40):                                           # tensor core may flush operands
+            rows.append((rs.standard_normal(d) * sc).astype(np.float32))
+    for _ in range(40):                                               # mixed: one normal element, rest denormal
+        r = (rs.standard_normal(d) * 1e-40).astype(np.float32)
+        r[rs.randint(d)] = np.float32(2e-38)
+        rows.append(r)
+    rows.append(np.full(d, -0.0, np.float32))                         # all negative zeros
     x = np.stack(rows * 8).astype(np.float32)
     oc, ou = O.hsq_search(x, cb)
     for algo in (_lib.ALGO_EXACT, _lib.ALGO_AUTO):
