@@ -41,7 +41,13 @@ constexpr int kGroup = 4;                         // codewords per rescoring gro
 constexpr int kNumGroups = kK / kGroup;           // 64
 constexpr uint32_t kPlaneBytes = kK * 128;        // one rescoring plane: 128-byte slot per codeword
 constexpr int kPlanes = 4;
-constexpr float kMargin = 3.0f / 512.0f;          // 2 * eps / ||v||
+// Rescoring margin, 2 * eps / (||v|| max_k ||c_k||).  The tensor core reads the top 19 bits of an
+// fp32 operand (TF32, truncation -- measured: adding the two truncation remainders back with extra
+// MMAs leaves a residual of 1.1e-6 ||v||), so every product is off by at most 2^-9 |v_j c_kj|
+// whatever the rounding of either operand, the sum by at most 2^-9 ||v|| ||c_k|| (Cauchy-Schwarz);
+// the fp32 accumulation of 16 terms adds < 16 * 2^-23 ||v|| ||c_k||; 4e-6 covers that, the
+// rounding of ||v|| and of the threshold itself.  Largest error measured: 1.15e-3 ||v||.
+constexpr float kMargin = 2.0f * (1.0f / 512.0f + 4.0e-6f);
 
 static_assert(kStages % 2 == 0 && kStages % 3 == 0, "barrier ring must be a multiple of the buffer and group counts");
 constexpr uint32_t kOffA = 0;
@@ -221,6 +227,8 @@ hsq_search_tc_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_
     const uint32_t bar_tempty = bar_tfull + 8 * kStages;
     const uint32_t bar_cb = bar_tempty + 8 * kStages;
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(smem + kOffBar + 8 * (4 * kStages + 1));
+    float *s_cn2 = reinterpret_cast<float *>(smem + kOffBar + 8 * (4 * kStages + 1) + 8);   // [8] per-warp max ||c_k||^2
+    static_assert(8 * (4 * kStages + 1) + 8 + 32 <= 256, "barrier region");
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -255,6 +263,19 @@ hsq_search_tc_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_
         const float4 val = __ldg(reinterpret_cast<const float4 *>(codebook) + k * 4 + u);
         *reinterpret_cast<float4 *>(s_planes + r * kPlaneBytes + k * 128 + 16 * (4 * h + ((u + r) & 3))) = val;
     }
+    // largest codeword norm: the error bound (hence the margin) scales with it, so the search stays
+    // exact for a codebook that is not unit-norm; a non-finite codebook disables the filter
+    if (threadIdx.x < kK) {
+        float c2 = 0.0f;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float4 t = __ldg(reinterpret_cast<const float4 *>(codebook) + threadIdx.x * 4 + u);
+            c2 = fmaf(t.x, t.x, c2); c2 = fmaf(t.y, t.y, c2); c2 = fmaf(t.z, t.z, c2); c2 = fmaf(t.w, t.w, c2);
+        }
+        if (!(c2 < 3.0e38f)) c2 = __int_as_float(0x7f800000);   // NaN -> +inf so that the max keeps it
+        c2 = warp_max(c2);
+        if (lane == 0) s_cn2[warp] = c2;
+    }
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
@@ -263,6 +284,11 @@ hsq_search_tc_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
+    float cn2 = s_cn2[0];
+#pragma unroll
+    for (int w = 1; w < kK / 32; ++w) cn2 = fmaxf(cn2, s_cn2[w]);
+    // (a non-finite codebook gives margin = +inf: threshold -inf, every group is rescored)
+    const float margin = kMargin * (1.0f + 1.0e-5f) * sqrtf(cn2);
     // everything above (barrier init, codebook planes, TMEM allocation) reads only the static
     // codebook and overlaps the tail of the previous kernel; the gradient, the min/max keys and
     // the output buffers are touched only after this point
@@ -410,7 +436,7 @@ hsq_search_tc_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_
                 for (int g = 2; g < 16; g += 2) am[q] = fmaxf(am[q], fmaxf(gm[16 * q + g], gm[16 * q + g + 1]));
             }
             const float amax = fmaxf(fmaxf(am[0], am[1]), fmaxf(am[2], am[3]));
-            const float thr = amax - kMargin * sqrtf(n2);
+            const float thr = amax - margin * sqrtf(n2);
             // candidate groups: gm[g] >= thr.  d = gm - thr on the FMA pipe, sign bits funnelled
             // into two 32-bit words (bit g of below[g >> 5] set = group g is below the threshold).
             uint32_t bl[4] = {0u, 0u, 0u, 0u};   // four independent chains of 16 groups each

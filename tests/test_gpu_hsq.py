@@ -95,6 +95,39 @@ def test_hsq_adversarial_ties_and_specials():
         assert np.array_equal(u.cpu().numpy(), ou), algo
 
 
+def _raw_search(x, cb, algo):
+    n_chunks, d = x.shape
+    xt, cbt = _t(x), _t(cb)
+    codes = torch.full((n_chunks,), 255, dtype=torch.uint8, device=DEV)
+    u = torch.zeros(n_chunks, device=DEV)
+    seg = torch.tensor([0, n_chunks], dtype=torch.int64, device=DEV)
+    ws = torch.empty(1 << 20, dtype=torch.uint8, device=DEV)
+    _lib.call("gq_hsq_search", xt.data_ptr(), n_chunks, d, cbt.data_ptr(), cb.shape[0], codes.data_ptr(), 1,
+              u.data_ptr(), seg.data_ptr(), 1, None, ws.data_ptr(), ws.numel(), algo, _lib.stream())
+    torch.cuda.synchronize()
+    return codes.cpu().numpy().astype(np.int32), u.cpu().numpy()
+
+
+@pytest.mark.parametrize("scale", ["x3.7", "rows", "tiny"])
+def test_hsq_search_exact_for_codebooks_that_are_not_unit_norm(scale):
+    """The tensor-core filter's margin follows the largest codeword norm, so the C entry point stays
+    bit-exact when the caller's codebook is not normalised (the reference always normalises)."""
+    rs = np.random.RandomState(11)
+    cb = codebook(16, 256).copy()
+    if scale == "x3.7":
+        cb *= np.float32(3.7)
+    elif scale == "rows":
+        cb *= rs.uniform(0.05, 20.0, size=(256, 1)).astype(np.float32)
+    else:
+        cb *= np.float32(1e-12)
+    x = gen_input(77, 30011 * 16, "normal").reshape(-1, 16)
+    oc, ou = O.hsq_search(x, cb)
+    for algo in (_lib.ALGO_EXACT, _lib.ALGO_AUTO):
+        gc, gu = _raw_search(x, cb, algo)
+        assert np.array_equal(gc, oc), (scale, algo)
+        assert np.array_equal(gu, ou), (scale, algo)
+
+
 def test_hsq_nonfinite_inputs_do_not_hang_and_match_nan_rule():
     d, K = 16, 256
     x = gen_input(77, 256 * d).reshape(-1, d).copy()
