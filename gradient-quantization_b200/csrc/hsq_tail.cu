@@ -7,6 +7,8 @@
 //        ring_quantizer.py:31-32)
 // All HBM-bound.  Algorithmic bytes per gradient element (d = chunk dim, U users):
 //   quantize: (4 u + 1 l [+4 r]) / d        decode-reduce: 4 + 2U/d (+4 if accumulate)
+#include <stdlib.h>
+
 #include "gq_internal.cuh"
 
 namespace gq {
@@ -77,68 +79,79 @@ norm_quantize_smem_kernel(const float *__restrict__ u, int64_t n, const int64_t 
         s_lbub[i] = f;
         if (blockIdx.x == 0) lbub[i] = f;
     }
-    const int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    // Each thread handles groups of four chunks a grid-width apart (coalesced); the host sizes the
+    // grid so that it is ONE resident wave with the items spread evenly (1435 blocks of one item
+    // each were 1.2 waves on 148 SMs: the second, nearly empty wave doubled the run time).  The
+    // loads of the next item are issued before the current one is processed.
     const int64_t n4 = (n + 3) / 4;
-    // prefetch this thread's data while the tables land
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x;
     float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), rv = make_float4(0.f, 0.f, 0.f, 0.f);
-    const bool in = q < n4;
-    const bool full = in && (q * 4 + 3 < n);
-    if (full) {
+    if (q < n4 && q * 4 + 3 < n) {
         xv = __ldg(reinterpret_cast<const float4 *>(u) + q);
         if (random && uniforms) rv = __ldg(reinterpret_cast<const float4 *>(uniforms) + q);
     }
     __syncthreads();
-    if (!in) return;
-    const int64_t i0 = q * 4;
-    float x[4] = {xv.x, xv.y, xv.z, xv.w}, r[4] = {rv.x, rv.y, rv.z, rv.w};
-    if (!full) {
+    for (; q < n4; q += stride) {
+        const bool full = q * 4 + 3 < n;
+        const int64_t i0 = q * 4;
+        float x[4] = {xv.x, xv.y, xv.z, xv.w}, r[4] = {rv.x, rv.y, rv.z, rv.w};
+        {
+            const int64_t qn = q + stride;
+            if (qn < n4 && qn * 4 + 3 < n) {
+                xv = __ldg(reinterpret_cast<const float4 *>(u) + qn);
+                if (random && uniforms) rv = __ldg(reinterpret_cast<const float4 *>(uniforms) + qn);
+            }
+        }
+        if (!full) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                x[t] = (i0 + t < n) ? u[i0 + t] : 0.0f;
+                r[t] = (random && uniforms && i0 + t < n) ? uniforms[i0 + t] : 0.0f;
+            }
+        }
+        if (random && !uniforms) {
+            if (((offset + (uint64_t)i0) & 3u) == 0) {
+                const uint4 w = philox4x32_10(seed, (offset + (uint64_t)i0) >> 2);
+                r[0] = u01(w.x); r[1] = u01(w.y); r[2] = u01(w.z); r[3] = u01(w.w);
+            } else {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) r[t] = philox_uniform(seed, offset, (uint64_t)(i0 + t));
+            }
+        }
+        // segment of the first chunk by binary search in shared memory, then walk forward
+        int seg = 0;
+        {
+            int lo = 0, hi = n_seg;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (s_seg[mid] <= i0) lo = mid; else hi = mid;
+            }
+            seg = lo;
+        }
+        int lv[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-            x[t] = (i0 + t < n) ? u[i0 + t] : 0.0f;
-            r[t] = (random && uniforms && i0 + t < n) ? uniforms[i0 + t] : 0.0f;
+            const int64_t i = i0 + t;
+            if (i < n) {
+                while (i >= s_seg[seg + 1]) ++seg;
+                lv[t] = psc_level(x[t], s_lbub[2 * seg], s_lbub[2 * seg + 1], s, random, r[t]);
+            } else {
+                lv[t] = 0;
+            }
         }
-    }
-    if (random && !uniforms) {
-        if (((offset + (uint64_t)i0) & 3u) == 0) {
-            const uint4 w = philox4x32_10(seed, (offset + (uint64_t)i0) >> 2);
-            r[0] = u01(w.x); r[1] = u01(w.y); r[2] = u01(w.z); r[3] = u01(w.w);
+        if (full) {
+            if (sizeof(LT) == 1) {
+                reinterpret_cast<uint32_t *>(l)[q] =
+                    (uint32_t)lv[0] | ((uint32_t)lv[1] << 8) | ((uint32_t)lv[2] << 16) | ((uint32_t)lv[3] << 24);
+            } else {
+                reinterpret_cast<int4 *>(l)[q] = make_int4(lv[0], lv[1], lv[2], lv[3]);
+            }
         } else {
 #pragma unroll
-            for (int t = 0; t < 4; ++t) r[t] = philox_uniform(seed, offset, (uint64_t)(i0 + t));
+            for (int t = 0; t < 4; ++t)
+                if (i0 + t < n) l[i0 + t] = (LT)lv[t];
         }
-    }
-    // segment of the first chunk by binary search in shared memory, then walk forward
-    int seg = 0;
-    {
-        int lo = 0, hi = n_seg;
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (s_seg[mid] <= i0) lo = mid; else hi = mid;
-        }
-        seg = lo;
-    }
-    int lv[4];
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-        const int64_t i = i0 + t;
-        if (i < n) {
-            while (i >= s_seg[seg + 1]) ++seg;
-            lv[t] = psc_level(x[t], s_lbub[2 * seg], s_lbub[2 * seg + 1], s, random, r[t]);
-        } else {
-            lv[t] = 0;
-        }
-    }
-    if (full) {
-        if (sizeof(LT) == 1) {
-            reinterpret_cast<uint32_t *>(l)[q] =
-                (uint32_t)lv[0] | ((uint32_t)lv[1] << 8) | ((uint32_t)lv[2] << 16) | ((uint32_t)lv[3] << 24);
-        } else {
-            reinterpret_cast<int4 *>(l)[q] = make_int4(lv[0], lv[1], lv[2], lv[3]);
-        }
-    } else {
-#pragma unroll
-        for (int t = 0; t < 4; ++t)
-            if (i0 + t < n) l[i0 + t] = (LT)lv[t];
     }
 }
 
@@ -184,7 +197,15 @@ int launch_norm_quantize(const float *u, int64_t n, const int64_t *seg_start, in
     if (n_seg <= kQuantMaxSeg && aligned && n4 > 0 && n4 < ((int64_t)1 << 31) * 256) {
         // one thread per four chunks, tables in shared memory
         const size_t smem = (size_t)(n_seg + 1) * 8 + (size_t)n_seg * 8;
-        const unsigned grid = (unsigned)((n4 + 255) / 256);
+        const int64_t blocks = (n4 + 255) / 256;
+        int occ = 1;
+        if (l_bytes == 1)
+            GQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, norm_quantize_smem_kernel<uint8_t>, 256, smem));
+        else
+            GQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, norm_quantize_smem_kernel<int32_t>, 256, smem));
+        const int64_t cap = (int64_t)sm_count() * (occ < 1 ? 1 : occ);
+        const int64_t items = (blocks + cap - 1) / cap;                    // per thread
+        const unsigned grid = (unsigned)((blocks + items - 1) / items);    // one wave, evenly loaded
         if (l_bytes == 1)
             GQ_CUDA(launch_pdl(norm_quantize_smem_kernel<uint8_t>, dim3(grid), dim3(256), smem, st, u, n, seg_start,
                                n_seg, s, random, uniforms, seed, offset, (uint8_t *)l, lbub, keys));
@@ -497,6 +518,173 @@ hsq_decode_reduce_warp_kernel(const CodeT *__restrict__ codes, const LT *__restr
     }
 }
 
+// Pull-and-decode for records that live in DIFFERENT buffers (one per user, typically peer GPU
+// memory mapped over NVLink): d = 16, uint8 codes and levels.  Each CTA walks tiles of 1024 chunks;
+// the code / level bytes of all users for the next tile are pulled with 16-byte cp.async (wide
+// requests, bypassing L1) into a double-buffered shared-memory stage while the current tile is
+// decoded, so every remote byte crosses NVLink exactly once and the transfer overlaps the decode:
+// the exchange step needs no separate gather pass and no local copy of the peers' records.
+// The lb/ub tables of all users are staged once per CTA.  The codebook is stored twice per
+// codeword (128-byte slots): lanes 0-3 of a quarter-warp read the copy in bank groups 0-3, lanes
+// 4-7 the copy in groups 4-7, so the two codewords a quarter-warp gathers never conflict.
+constexpr int kStTile = 1024;
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gsrc) : "memory");
+}
+template <int MAXU>
+__global__ void __launch_bounds__(kDecodeThreads)
+hsq_decode_reduce_staged_kernel(const uint8_t *__restrict__ codes, const uint8_t *__restrict__ l,
+                                const float *__restrict__ lbub, const UserOffsets uoff, int n_users,
+                                int64_t n_chunks, const float *__restrict__ codebook,
+                                const int64_t *__restrict__ seg_start, int n_seg, float s, int mean,
+                                int accumulate, float *__restrict__ out)
+{
+    extern __shared__ float4 s_dyn[];
+    float4 *s_cb = s_dyn;                                                    // [256][2][4]
+    uint8_t *s_stage = reinterpret_cast<uint8_t *>(s_cb + 256 * 8);          // [2][MAXU][codes 1024 | l 1024]
+    float2 *s_lbub = reinterpret_cast<float2 *>(s_stage + 2 * MAXU * 2 * kStTile);   // [n_users][n_seg]
+    __shared__ int64_t s_off[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_launch_dependents();
+    if (tid == 0) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s_off[u] = uoff.off[u];
+    }
+    for (int i = tid; i < 256 * 8; i += kDecodeThreads)
+        s_cb[i] = __ldg(reinterpret_cast<const float4 *>(codebook) + (i >> 3) * 4 + (i & 3));
+    __syncthreads();
+    pdl_wait();   // the records are complete (and, across GPUs, announced by the barrier kernel)
+    for (int i = tid; i < n_users * n_seg; i += kDecodeThreads) {
+        const int u = i / n_seg, sg = i - u * n_seg;
+        const float2 *b = reinterpret_cast<const float2 *>(reinterpret_cast<const char *>(lbub) + s_off[u]);
+        s_lbub[i] = __ldcv(b + sg);
+    }
+    const int64_t n_tiles = (n_chunks + kStTile - 1) / kStTile;
+    auto issue = [&](int64_t tile, int buf) {
+        const int64_t c0 = tile * kStTile;
+        const int64_t left = n_chunks - c0;
+        const int pieces = (int)(((left < kStTile ? left : (int64_t)kStTile) + 15) >> 4);   // 16-byte pieces holding data
+        for (int i = tid; i < n_users * 128; i += kDecodeThreads) {
+            const int u = i >> 7, which = (i >> 6) & 1, piece = i & 63;
+            if (piece < pieces) {
+                const char *src = (which ? reinterpret_cast<const char *>(l) : reinterpret_cast<const char *>(codes)) +
+                                  s_off[u] + c0 + piece * 16;
+                cp_async16(s_stage + ((buf * MAXU + u) * 2 + which) * kStTile + piece * 16, src);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const float inv_s = 1.0f / s;
+    const float nu = (float)n_users;
+    const bool pow2 = (n_users & (n_users - 1)) == 0;
+    const float inv_nu = 1.0f / nu;
+    const int half = (lane >> 2) & 1, part = lane & 3;
+    SegCache segc;
+    float4 *o4 = reinterpret_cast<float4 *>(out);
+    const int64_t n4 = n_chunks * 4;
+    int64_t tile = blockIdx.x;
+    int buf = 0;
+    if (tile < n_tiles) issue(tile, 0);
+    for (; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
+        const int64_t next = tile + gridDim.x;
+        if (next < n_tiles) {
+            issue(next, buf ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const uint8_t *st = s_stage + (size_t)buf * MAXU * 2 * kStTile;
+        const int64_t c0 = tile * kStTile;
+        for (int sl = warp; sl < kStTile / 32; sl += kDecodeThreads / 32) {
+            const int64_t c = c0 + sl * 32 + lane;
+            if (c0 + sl * 32 >= n_chunks) break;
+            const bool ok = c < n_chunks;
+            const int seg = ok ? cached_segment(segc, seg_start, n_seg, c) : 0;
+            int code[MAXU];
+            float nrm[MAXU];
+#pragma unroll
+            for (int u = 0; u < MAXU; ++u) {
+                code[u] = 0;
+                nrm[u] = 0.0f;
+                if (u < n_users) {
+                    code[u] = (int)st[(u * 2) * kStTile + sl * 32 + lane];
+                    const float lv = (float)(int)st[(u * 2 + 1) * kStTile + sl * 32 + lane];
+                    const float2 b = s_lbub[u * n_seg + seg];
+                    // l * (ub - lb) / 2^n + lb   (probabilistic_scalar_compressor.py:31-32)
+                    nrm[u] = __fadd_rn(__fmul_rn(__fmul_rn(lv, __fsub_rn(b.y, b.x)), inv_s), b.x);
+                }
+            }
+            const int64_t f0 = (c0 + sl * 32) * 4;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int owner = r * 8 + (lane >> 2);
+                float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int u = 0; u < MAXU; ++u) {
+                    if (u < n_users) {
+                        const int cd = __shfl_sync(0xffffffffu, code[u], owner);
+                        const float nm = __shfl_sync(0xffffffffu, nrm[u], owner);
+                        const float4 cw = s_cb[cd * 8 + half * 4 + part];
+                        const float2 p0 = mul2(make_float2(cw.x, cw.y), nm);
+                        const float2 p1 = mul2(make_float2(cw.z, cw.w), nm);
+                        if (u == 0) {
+                            a0 = p0; a1 = p1;
+                        } else {   // scalar adds: see hsq_decode_reduce_warp_kernel
+                            a0.x = __fadd_rn(a0.x, p0.x); a0.y = __fadd_rn(a0.y, p0.y);
+                            a1.x = __fadd_rn(a1.x, p1.x); a1.y = __fadd_rn(a1.y, p1.y);
+                        }
+                    }
+                }
+                float4 acc = make_float4(a0.x, a0.y, a1.x, a1.y);
+                const int64_t f = f0 + r * 32 + lane;
+                if (f < n4) {
+                    if (mean && n_users > 1) {
+                        if (pow2) {
+                            acc.x = __fmul_rn(acc.x, inv_nu); acc.y = __fmul_rn(acc.y, inv_nu);
+                            acc.z = __fmul_rn(acc.z, inv_nu); acc.w = __fmul_rn(acc.w, inv_nu);
+                        } else {
+                            acc.x = __fdiv_rn(acc.x, nu); acc.y = __fdiv_rn(acc.y, nu);
+                            acc.z = __fdiv_rn(acc.z, nu); acc.w = __fdiv_rn(acc.w, nu);
+                        }
+                    }
+                    if (accumulate) {
+                        const float4 o = o4[f];
+                        acc.x = __fadd_rn(o.x, acc.x); acc.y = __fadd_rn(o.y, acc.y);
+                        acc.z = __fadd_rn(o.z, acc.z); acc.w = __fadd_rn(o.w, acc.w);
+                    }
+                    o4[f] = acc;
+                }
+            }
+        }
+        __syncthreads();   // this stage buffer is refilled by the next iteration's prefetch
+    }
+}
+
+template <int MAXU>
+static int launch_decode_staged(const void *codes, const void *l, const float *lbub, const UserOffsets &uoff,
+                                int n_users, int64_t n_chunks, const float *codebook, const int64_t *seg_start,
+                                int n_seg, float s, int mean, int accumulate, float *out, cudaStream_t st)
+{
+    auto kern = hsq_decode_reduce_staged_kernel<MAXU>;
+    const size_t smem = 256 * 128 + (size_t)2 * MAXU * 2 * kStTile + (size_t)n_users * n_seg * 8;
+    GQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    GQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kDecodeThreads, smem));
+    const int64_t n_tiles = (n_chunks + kStTile - 1) / kStTile;
+    const int64_t cap = (int64_t)sm_count() * (occ < 1 ? 1 : occ);
+    // an even number of tiles per CTA: size the grid so that no CTA is left with one tile more
+    const int64_t per = (n_tiles + cap - 1) / cap;
+    int64_t grid = (n_tiles + per - 1) / per;
+    if (grid < 1) grid = 1;
+    GQ_CUDA(launch_pdl(kern, dim3((unsigned)grid), dim3(kDecodeThreads), smem, st, (const uint8_t *)codes,
+                       (const uint8_t *)l, lbub, uoff, n_users, n_chunks, codebook, seg_start, n_seg, s, mean,
+                       accumulate, out));
+    return GQ_OK;
+}
+
 template <int D, int MAXU, typename CodeT, typename LT>
 static int launch_decode_warp(const void *codes, const void *l, const float *lbub, const float *norms_f32,
                               const UserOffsets &uoff, int n_users, int64_t n_chunks, const float *codebook,
@@ -535,6 +723,21 @@ static int launch_decode_d(const void *codes, const void *l, const float *lbub, 
         UserOffsets uoff;
         for (int u = 0; u < 8; ++u)
             uoff.off[u] = (u < n_users) ? (user_offsets ? user_offsets[u] : (int64_t)u * user_stride) : 0;
+        // records in separate (peer) buffers: pull-and-decode through a shared-memory stage
+        bool staged = user_offsets != nullptr;
+        if (const char *e = getenv("GQ_DECODE_STAGED")) staged = atoi(e) != 0;
+        if (staged && D == 16 && K == 256 && sizeof(CodeT) == 1 && sizeof(LT) == 1 && n_bit != 32 &&
+            (size_t)n_users * n_seg * 8 <= 48 * 1024) {
+            bool aligned = (((uintptr_t)codes | (uintptr_t)l | (uintptr_t)lbub) & 15) == 0;
+            for (int u = 0; u < n_users; ++u) aligned = aligned && ((uoff.off[u] & 15) == 0);
+            if (aligned) {
+#define GQ_S(MU) return launch_decode_staged<MU>(codes, l, lbub, uoff, n_users, n_chunks, codebook, seg_start, n_seg, s, mean, accumulate, out, st)
+                if (n_users <= 2) GQ_S(2);
+                if (n_users <= 4) GQ_S(4);
+                GQ_S(8);
+#undef GQ_S
+            }
+        }
 #define GQ_W(MU) return launch_decode_warp<DW, MU, CodeT, LT>(codes, l, lbub, norms_f32, uoff, n_users, n_chunks, codebook, K, seg_start, n_seg, s, n_bit, mean, accumulate, out, st)
         if (n_users == 1) GQ_W(1);
         if (n_users == 2) GQ_W(2);
