@@ -533,20 +533,36 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
                  "l"(gsrc) : "memory");
 }
-template <int MAXU>
+__device__ __forceinline__ float4 lds128(uint32_t saddr)
+{
+    float4 r;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(saddr));
+    return r;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t saddr)
+{
+    uint32_t r;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(r) : "r"(saddr) : "memory");
+    return r;
+}
+// NU = exact number of users (compile time: the per-user loops are branch-free)
+template <int NU>
 __global__ void __launch_bounds__(kDecodeThreads)
 hsq_decode_reduce_staged_kernel(const uint8_t *__restrict__ codes, const uint8_t *__restrict__ l,
-                                const float *__restrict__ lbub, const UserOffsets uoff, int n_users,
+                                const float *__restrict__ lbub, const UserOffsets uoff,
                                 int64_t n_chunks, const float *__restrict__ codebook,
                                 const int64_t *__restrict__ seg_start, int n_seg, float s, int mean,
                                 int accumulate, float *__restrict__ out)
 {
     extern __shared__ float4 s_dyn[];
     float4 *s_cb = s_dyn;                                                    // [256][2][4]
-    uint8_t *s_stage = reinterpret_cast<uint8_t *>(s_cb + 256 * 8);          // [2][MAXU][codes 1024 | l 1024]
-    float2 *s_lbub = reinterpret_cast<float2 *>(s_stage + 2 * MAXU * 2 * kStTile);   // [n_users][n_seg]
+    uint8_t *s_stage = reinterpret_cast<uint8_t *>(s_cb + 256 * 8);          // [2][NU][codes 1024 | l 1024]
+    float2 *s_lbub = reinterpret_cast<float2 *>(s_stage + 2 * NU * 2 * kStTile);   // [NU][n_seg]
     __shared__ int64_t s_off[8];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    // warp index through a shuffle: the compiler then knows it is warp-uniform, and the slot loop
+    // below (with its warp shuffles) is compiled as convergent code
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     pdl_launch_dependents();
     if (tid == 0) {
 #pragma unroll
@@ -556,7 +572,7 @@ hsq_decode_reduce_staged_kernel(const uint8_t *__restrict__ codes, const uint8_t
         s_cb[i] = __ldg(reinterpret_cast<const float4 *>(codebook) + (i >> 3) * 4 + (i & 3));
     __syncthreads();
     pdl_wait();   // the records are complete (and, across GPUs, announced by the barrier kernel)
-    for (int i = tid; i < n_users * n_seg; i += kDecodeThreads) {
+    for (int i = tid; i < NU * n_seg; i += kDecodeThreads) {
         const int u = i / n_seg, sg = i - u * n_seg;
         const float2 *b = reinterpret_cast<const float2 *>(reinterpret_cast<const char *>(lbub) + s_off[u]);
         s_lbub[i] = __ldcv(b + sg);
@@ -566,21 +582,23 @@ hsq_decode_reduce_staged_kernel(const uint8_t *__restrict__ codes, const uint8_t
         const int64_t c0 = tile * kStTile;
         const int64_t left = n_chunks - c0;
         const int pieces = (int)(((left < kStTile ? left : (int64_t)kStTile) + 15) >> 4);   // 16-byte pieces holding data
-        for (int i = tid; i < n_users * 128; i += kDecodeThreads) {
+        for (int i = tid; i < NU * 128; i += kDecodeThreads) {
             const int u = i >> 7, which = (i >> 6) & 1, piece = i & 63;
             if (piece < pieces) {
                 const char *src = (which ? reinterpret_cast<const char *>(l) : reinterpret_cast<const char *>(codes)) +
                                   s_off[u] + c0 + piece * 16;
-                cp_async16(s_stage + ((buf * MAXU + u) * 2 + which) * kStTile + piece * 16, src);
+                cp_async16(s_stage + ((buf * NU + u) * 2 + which) * kStTile + piece * 16, src);
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     const float inv_s = 1.0f / s;
-    const float nu = (float)n_users;
-    const bool pow2 = (n_users & (n_users - 1)) == 0;
+    const float nu = (float)NU;
+    constexpr bool pow2 = (NU & (NU - 1)) == 0;
     const float inv_nu = 1.0f / nu;
-    const int half = (lane >> 2) & 1, part = lane & 3;
+    // 32-bit shared-window addresses: this lane's 16-byte unit inside a codeword slot, the stage
+    const uint32_t cb_lane = (uint32_t)__cvta_generic_to_shared(s_cb) + (uint32_t)(((lane >> 2) & 1) * 64 + (lane & 3) * 16);
+    const uint32_t stage0 = (uint32_t)__cvta_generic_to_shared(s_stage);
     SegCache segc;
     float4 *o4 = reinterpret_cast<float4 *>(out);
     const int64_t n4 = n_chunks * 4;
@@ -596,52 +614,49 @@ hsq_decode_reduce_staged_kernel(const uint8_t *__restrict__ codes, const uint8_t
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
-        const uint8_t *st = s_stage + (size_t)buf * MAXU * 2 * kStTile;
+        const uint32_t st = stage0 + (uint32_t)(buf * NU * 2 * kStTile);
         const int64_t c0 = tile * kStTile;
         for (int sl = warp; sl < kStTile / 32; sl += kDecodeThreads / 32) {
             const int64_t c = c0 + sl * 32 + lane;
             if (c0 + sl * 32 >= n_chunks) break;
             const bool ok = c < n_chunks;
             const int seg = ok ? cached_segment(segc, seg_start, n_seg, c) : 0;
-            int code[MAXU];
-            float nrm[MAXU];
+            uint32_t code[NU];
+            float nrm[NU];
 #pragma unroll
-            for (int u = 0; u < MAXU; ++u) {
-                code[u] = 0;
-                nrm[u] = 0.0f;
-                if (u < n_users) {
-                    code[u] = (int)st[(u * 2) * kStTile + sl * 32 + lane];
-                    const float lv = (float)(int)st[(u * 2 + 1) * kStTile + sl * 32 + lane];
-                    const float2 b = s_lbub[u * n_seg + seg];
-                    // l * (ub - lb) / 2^n + lb   (probabilistic_scalar_compressor.py:31-32)
-                    nrm[u] = __fadd_rn(__fmul_rn(__fmul_rn(lv, __fsub_rn(b.y, b.x)), inv_s), b.x);
-                }
+            for (int u = 0; u < NU; ++u) {
+                code[u] = lds_u8(st + (uint32_t)((u * 2) * kStTile + sl * 32 + lane)) << 7;   // byte offset of the slot
+                const float lv = (float)(int)lds_u8(st + (uint32_t)((u * 2 + 1) * kStTile + sl * 32 + lane));
+                const float2 b = s_lbub[u * n_seg + seg];
+                // l * (ub - lb) / 2^n + lb   (probabilistic_scalar_compressor.py:31-32)
+                nrm[u] = __fadd_rn(__fmul_rn(__fmul_rn(lv, __fsub_rn(b.y, b.x)), inv_s), b.x);
             }
             const int64_t f0 = (c0 + sl * 32) * 4;
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
                 const int owner = r * 8 + (lane >> 2);
-                float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+                float4 cw[NU];
+                float nm[NU];
 #pragma unroll
-                for (int u = 0; u < MAXU; ++u) {
-                    if (u < n_users) {
-                        const int cd = __shfl_sync(0xffffffffu, code[u], owner);
-                        const float nm = __shfl_sync(0xffffffffu, nrm[u], owner);
-                        const float4 cw = s_cb[cd * 8 + half * 4 + part];
-                        const float2 p0 = mul2(make_float2(cw.x, cw.y), nm);
-                        const float2 p1 = mul2(make_float2(cw.z, cw.w), nm);
-                        if (u == 0) {
-                            a0 = p0; a1 = p1;
-                        } else {   // scalar adds: see hsq_decode_reduce_warp_kernel
-                            a0.x = __fadd_rn(a0.x, p0.x); a0.y = __fadd_rn(a0.y, p0.y);
-                            a1.x = __fadd_rn(a1.x, p1.x); a1.y = __fadd_rn(a1.y, p1.y);
-                        }
-                    }
+                for (int u = 0; u < NU; ++u) {
+                    const uint32_t cd = __shfl_sync(0xffffffffu, code[u], owner);
+                    nm[u] = __shfl_sync(0xffffffffu, nrm[u], owner);
+                    cw[u] = lds128(cb_lane + cd);
+                }
+                float2 a0 = mul2(make_float2(cw[0].x, cw[0].y), nm[0]);
+                float2 a1 = mul2(make_float2(cw[0].z, cw[0].w), nm[0]);
+#pragma unroll
+                for (int u = 1; u < NU; ++u) {
+                    const float2 p0 = mul2(make_float2(cw[u].x, cw[u].y), nm[u]);
+                    const float2 p1 = mul2(make_float2(cw[u].z, cw[u].w), nm[u]);
+                    // scalar adds: see hsq_decode_reduce_warp_kernel
+                    a0.x = __fadd_rn(a0.x, p0.x); a0.y = __fadd_rn(a0.y, p0.y);
+                    a1.x = __fadd_rn(a1.x, p1.x); a1.y = __fadd_rn(a1.y, p1.y);
                 }
                 float4 acc = make_float4(a0.x, a0.y, a1.x, a1.y);
                 const int64_t f = f0 + r * 32 + lane;
                 if (f < n4) {
-                    if (mean && n_users > 1) {
+                    if (mean && NU > 1) {
                         if (pow2) {
                             acc.x = __fmul_rn(acc.x, inv_nu); acc.y = __fmul_rn(acc.y, inv_nu);
                             acc.z = __fmul_rn(acc.z, inv_nu); acc.w = __fmul_rn(acc.w, inv_nu);
@@ -663,24 +678,24 @@ hsq_decode_reduce_staged_kernel(const uint8_t *__restrict__ codes, const uint8_t
     }
 }
 
-template <int MAXU>
+template <int NU>
 static int launch_decode_staged(const void *codes, const void *l, const float *lbub, const UserOffsets &uoff,
-                                int n_users, int64_t n_chunks, const float *codebook, const int64_t *seg_start,
+                                int64_t n_chunks, const float *codebook, const int64_t *seg_start,
                                 int n_seg, float s, int mean, int accumulate, float *out, cudaStream_t st)
 {
-    auto kern = hsq_decode_reduce_staged_kernel<MAXU>;
-    const size_t smem = 256 * 128 + (size_t)2 * MAXU * 2 * kStTile + (size_t)n_users * n_seg * 8;
+    auto kern = hsq_decode_reduce_staged_kernel<NU>;
+    const size_t smem = 256 * 128 + (size_t)2 * NU * 2 * kStTile + (size_t)NU * n_seg * 8;
     GQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 1;
     GQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kDecodeThreads, smem));
     const int64_t n_tiles = (n_chunks + kStTile - 1) / kStTile;
     const int64_t cap = (int64_t)sm_count() * (occ < 1 ? 1 : occ);
-    // an even number of tiles per CTA: size the grid so that no CTA is left with one tile more
+    // the same number of tiles for every CTA (to within one): no CTA is left with a straggler tile
     const int64_t per = (n_tiles + cap - 1) / cap;
     int64_t grid = (n_tiles + per - 1) / per;
     if (grid < 1) grid = 1;
     GQ_CUDA(launch_pdl(kern, dim3((unsigned)grid), dim3(kDecodeThreads), smem, st, (const uint8_t *)codes,
-                       (const uint8_t *)l, lbub, uoff, n_users, n_chunks, codebook, seg_start, n_seg, s, mean,
+                       (const uint8_t *)l, lbub, uoff, n_chunks, codebook, seg_start, n_seg, s, mean,
                        accumulate, out));
     return GQ_OK;
 }
@@ -724,17 +739,20 @@ static int launch_decode_d(const void *codes, const void *l, const float *lbub, 
         for (int u = 0; u < 8; ++u)
             uoff.off[u] = (u < n_users) ? (user_offsets ? user_offsets[u] : (int64_t)u * user_stride) : 0;
         // records in separate (peer) buffers: pull-and-decode through a shared-memory stage
-        bool staged = user_offsets != nullptr;
+        // and for local records as well: measured faster than the warp kernel for every U
+        // (U = 1: 23 vs 27 us, U = 8: 76 vs 83 us on the ResNet-50 record); GQ_DECODE_STAGED=0 = old path
+        bool staged = true;
         if (const char *e = getenv("GQ_DECODE_STAGED")) staged = atoi(e) != 0;
         if (staged && D == 16 && K == 256 && sizeof(CodeT) == 1 && sizeof(LT) == 1 && n_bit != 32 &&
             (size_t)n_users * n_seg * 8 <= 48 * 1024) {
             bool aligned = (((uintptr_t)codes | (uintptr_t)l | (uintptr_t)lbub) & 15) == 0;
             for (int u = 0; u < n_users; ++u) aligned = aligned && ((uoff.off[u] & 15) == 0);
             if (aligned) {
-#define GQ_S(MU) return launch_decode_staged<MU>(codes, l, lbub, uoff, n_users, n_chunks, codebook, seg_start, n_seg, s, mean, accumulate, out, st)
-                if (n_users <= 2) GQ_S(2);
-                if (n_users <= 4) GQ_S(4);
-                GQ_S(8);
+#define GQ_S(MU) case MU: return launch_decode_staged<MU>(codes, l, lbub, uoff, n_chunks, codebook, seg_start, n_seg, s, mean, accumulate, out, st)
+                switch (n_users) {
+                    GQ_S(1); GQ_S(2); GQ_S(3); GQ_S(4); GQ_S(5); GQ_S(6); GQ_S(7); GQ_S(8);
+                    default: break;
+                }
 #undef GQ_S
             }
         }
