@@ -306,15 +306,7 @@ def main():
                   args.hsq_algo, st)
 
     def decode_only(i):
-        if q.p2p is not None and q.p2p_mode == "direct":
-            plan.decode(n_users=world, mean=True, out=outputs[i % ROT], base_ptr=q.p2p.user0_record_ptr(),
-                        user_offsets=q.p2p.user_offsets())
-        elif q.p2p is not None:
-            own, plan.records = plan.records, q._gathered
-            plan.decode(n_users=world, mean=True, out=outputs[i % ROT])
-            plan.records = own
-        else:
-            plan.decode(mean=True, out=outputs[i % ROT])
+        q.decode_exchanged(outputs[i % ROT])
 
     def time_loop(fn, iters):
         for i in range(3):
@@ -447,7 +439,7 @@ def main():
                    "elements_per_user": n_total, "compressed_elements": plan.compressed_elems(),
                    "users": world, "wire_bytes_per_user": plan.wire_bytes(), "algo": a.algo,
                    "exchange": ("none (1 user)" if world == 1 else
-                                ("peer-to-peer (%s): barrier kernel + pull of the peers' packed records over NVLink" % q.p2p_mode
+                                ("peer-to-peer (%s): packed records cross NVLink through peer-mapped memory, barrier kernel" % q.p2p_mode
                                  if q.p2p is not None else "NCCL all-gather of packed records")),
                    "l2": "inputs/outputs rotate over %d buffers of %.0f MB each (> 126 MB L2)"
                          % (ROT, plan.arena_elems * 4 / 1e6)},

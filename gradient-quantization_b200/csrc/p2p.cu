@@ -58,6 +58,37 @@ peer_gather_kernel(uint4 *__restrict__ dst, const PeerPtrs src, size_t n16, size
     for (; i < n16; i += step) d[i] = __ldcv(s + i);
 }
 
+struct PeerDst {
+    uint4 *p[8];
+};
+
+// push the local record into every peer's receive buffer: one local read, n_dst posted remote
+// stores per 16 bytes.  Stores over NVLink are fire-and-forget, so (unlike the pull in
+// peer_gather_kernel) no thread waits a round trip; the barrier kernel that follows on the stream
+// publishes them with its system-scope release.
+__global__ void __launch_bounds__(256)
+peer_push_kernel(const uint4 *__restrict__ src, const PeerDst dst, int n_dst, size_t n16)
+{
+    const size_t step = (size_t)gridDim.x * 256;
+    size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    for (; i + 3 * step < n16; i += 4 * step) {
+        const uint4 a = src[i], b = src[i + step], c = src[i + 2 * step], e = src[i + 3 * step];
+#pragma unroll
+        for (int d = 0; d < 8; ++d) {
+            if (d < n_dst) {
+                uint4 *o = dst.p[d];
+                o[i] = a; o[i + step] = b; o[i + 2 * step] = c; o[i + 3 * step] = e;
+            }
+        }
+    }
+    for (; i < n16; i += step) {
+        const uint4 a = src[i];
+#pragma unroll
+        for (int d = 0; d < 8; ++d)
+            if (d < n_dst) dst.p[d][i] = a;
+    }
+}
+
 }  // namespace gq
 
 extern "C" {
@@ -129,6 +160,28 @@ int gq_peer_gather(void *dst, void *const *src_ptrs, size_t bytes, size_t dst_st
     peer_gather_kernel<<<dim3(bx, n_ranks), 256, 0, as_stream(stream)>>>(reinterpret_cast<uint4 *>(dst), pp, n16,
                                                                           dst_stride / 16);
     GQ_LAUNCH_CHECK("peer_gather");
+    return GQ_OK;
+}
+
+// Before gq_peer_barrier: copy `bytes` (a multiple of 16) from the local `src` to each of the n_dst
+// addresses in dst_ptrs (host array of peer-mapped device addresses).
+int gq_peer_push(const void *src, void *const *dst_ptrs, size_t bytes, int n_dst, gq_stream_t stream)
+{
+    GQ_REQUIRE(src && dst_ptrs && n_dst >= 0 && n_dst <= 8, "bad arguments");
+    GQ_REQUIRE(bytes % 16 == 0 && ((uintptr_t)src & 15) == 0, "16-byte granularity");
+    if (n_dst == 0 || bytes == 0) return GQ_OK;
+    PeerDst pd;
+    for (int r = 0; r < 8; ++r) {
+        pd.p[r] = (r < n_dst) ? reinterpret_cast<uint4 *>(dst_ptrs[r]) : nullptr;
+        GQ_REQUIRE(r >= n_dst || (((uintptr_t)dst_ptrs[r] & 15) == 0 && dst_ptrs[r]), "bad destination");
+    }
+    const size_t n16 = bytes / 16;
+    int bx = (int)((n16 + 1023) / 1024);
+    const int cap = sm_count() * 2;
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    peer_push_kernel<<<bx, 256, 0, as_stream(stream)>>>(reinterpret_cast<const uint4 *>(src), pd, n_dst, n16);
+    GQ_LAUNCH_CHECK("peer_push");
     return GQ_OK;
 }
 

@@ -1,10 +1,15 @@
 """Peer-to-peer exchange of packed records (ps topology, one user per GPU, one NVSwitch node).
 
-Each rank owns one cudaMalloc'ed, IPC-exported buffer  [record 0 | record 1 | flags]  and maps
-every peer's buffer.  A step writes the local record of parity p, runs the barrier kernel
-(gq_peer_barrier) and then decodes all users' records of parity p straight out of peer memory.
-Double buffering makes one barrier per step sufficient: a rank can only overwrite record p two
-steps later, after every peer has passed the next barrier, i.e. finished reading it.
+Each rank owns one cudaMalloc'ed, IPC-exported buffer
+    [parity 0: U records | parity 1: U records | flags]
+and maps every peer's buffer.  A step encodes the local record straight into row `rank` of the
+current parity, then either
+  push   : stores it into row `rank` of every peer's buffer (posted NVLink writes), runs the
+           barrier kernel (gq_peer_barrier) and decodes its own, now complete, [U, record] block;
+  gather : runs the barrier, pulls every peer's row into the local block (wide loads), decodes;
+  direct : runs the barrier and lets the decode kernel pull the peers' rows itself.
+Double buffering makes one barrier per step sufficient: a row of parity p is overwritten two steps
+later, after every rank has passed the next barrier, i.e. finished reading that parity.
 """
 import ctypes
 
@@ -28,7 +33,7 @@ class PeerRecords:
     def __init__(self, record_bytes, rank, world, device):
         assert world <= 8
         self.record_bytes, self.rank, self.world, self.device = record_bytes, rank, world, device
-        total = 2 * record_bytes + self.FLAG_BYTES
+        total = 2 * world * record_bytes + self.FLAG_BYTES
         ptr = ctypes.c_void_p()
         handle = (ctypes.c_char * 64)()
         _lib.call("gq_ipc_alloc", total, ctypes.byref(ptr), ctypes.cast(handle, ctypes.c_void_p))
@@ -46,10 +51,10 @@ class PeerRecords:
                 _lib.call("gq_ipc_open", ctypes.cast(hbuf, ctypes.c_void_p), ctypes.byref(pp))
                 self.base.append(pp.value)
                 self._opened.append(pp.value)
-        self._holder = _CudaBuffer(self.local_ptr, 2 * record_bytes)
-        # [2, record_bytes] uint8 view of the local double buffer: the plan encodes into row `parity`
-        self.records = torch.as_tensor(self._holder, device=device).view(2, record_bytes)
-        self._flag_ptrs = (ctypes.c_void_p * world)(*[b + 2 * record_bytes for b in self.base])
+        self._holder = _CudaBuffer(self.local_ptr, 2 * world * record_bytes)
+        # [2 * U, record_bytes] uint8 view of the local buffer: row parity * U + user
+        self.records = torch.as_tensor(self._holder, device=device).view(2 * world, record_bytes)
+        self._flag_ptrs = (ctypes.c_void_p * world)(*[b + 2 * world * record_bytes for b in self.base])
         self.epoch = 0
         self.step = 0
         dist.barrier()   # every rank has mapped every buffer before anyone writes flags
@@ -63,18 +68,37 @@ class PeerRecords:
         _lib.call("gq_peer_barrier", ctypes.cast(self._flag_ptrs, ctypes.c_void_p), self.rank, self.world,
                   self.epoch, _lib.stream())
 
-    def gather(self, dst):
-        """Pull every user's record of the current parity into dst ([U, record_bytes], local)."""
-        srcs = (ctypes.c_void_p * self.world)(*[b + self.parity * self.record_bytes for b in self.base])
-        _lib.call("gq_peer_gather", dst.data_ptr(), ctypes.cast(srcs, ctypes.c_void_p), self.record_bytes,
-                  dst.stride(0), self.world, _lib.stream())
+    def row(self, user=None):
+        """Row of `records` holding `user`'s (default: this rank's) record of the current parity."""
+        return self.parity * self.world + (self.rank if user is None else user)
+
+    def _addr(self, owner, user):
+        return self.base[owner] + self.row(user) * self.record_bytes
+
+    def push(self):
+        """Store the local record into row `rank` of every peer's block (call before barrier())."""
+        if self.world == 1:
+            return
+        dsts = (ctypes.c_void_p * (self.world - 1))(*[self._addr(r, self.rank) for r in range(self.world)
+                                                       if r != self.rank])
+        _lib.call("gq_peer_push", self._addr(self.rank, self.rank), ctypes.cast(dsts, ctypes.c_void_p),
+                  self.record_bytes, self.world - 1, _lib.stream())
+
+    def gather(self):
+        """Pull every user's record of the current parity into the local block (after barrier());
+        one launch -- the own row is copied onto itself."""
+        srcs = (ctypes.c_void_p * self.world)(*[self._addr(r, r) for r in range(self.world)])
+        _lib.call("gq_peer_gather", self._addr(self.rank, 0), ctypes.cast(srcs, ctypes.c_void_p),
+                  self.record_bytes, self.record_bytes, self.world, _lib.stream())
 
     def user0_record_ptr(self):
-        return self.base[0] + self.parity * self.record_bytes
+        """direct mode: address of user 0's record in ITS OWNER's buffer."""
+        return self._addr(0, 0)
 
     def user_offsets(self):
-        """host int64 array: byte distance of user u's record from user 0's (any sign)."""
-        return (ctypes.c_int64 * self.world)(*[b - self.base[0] for b in self.base])
+        """host int64 array: byte distance of user u's record (in u's buffer) from user 0's."""
+        a0 = self._addr(0, 0)
+        return (ctypes.c_int64 * self.world)(*[self._addr(u, u) - a0 for u in range(self.world)])
 
     def advance(self):
         self.step += 1

@@ -51,12 +51,14 @@ class PSQuantizer(QuantizerBase):
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if int(flag.item()) == 1:
             self.p2p = p2p
-            # "gather" (default): pull the peers' records into the local [U, record_bytes] buffer with
-            # a wide-load copy kernel, then decode locally.  "direct": the decode kernel reads the
-            # peers' records itself (fewer bytes moved twice, but latency-bound byte loads over NVLink).
-            self.p2p_mode = os.environ.get("GQ_P2P_MODE", getattr(self.args, "p2p_mode", "gather"))
-            self._gathered = self.plan.records       # [U, record_bytes], local
-            self.plan.records = p2p.records          # [2, record_bytes]: row = step parity
+            # "push" (default): store the local record into every peer's block before the barrier
+            # (posted NVLink writes), decode locally.  "gather": pull the peers' records after the
+            # barrier with a wide-load copy kernel (reads pay a round trip: 15 vs 5 us at N = 2).
+            # "direct": the decode kernel pulls the peers' records itself through its cp.async stage.
+            self.p2p_mode = os.environ.get("GQ_P2P_MODE", getattr(self.args, "p2p_mode", "push"))
+            if self.p2p_mode not in ("push", "gather", "direct"):
+                raise _lib.GQError("unknown peer-to-peer mode %r" % (self.p2p_mode,))
+            self.plan.records = p2p.records          # [2 * U, record_bytes]: row = parity * U + user
         elif p2p is not None:
             p2p.close()
 
@@ -69,7 +71,7 @@ class PSQuantizer(QuantizerBase):
         if self.distributed and user != self.rank:
             raise _lib.GQError("distributed mode: rank %d records user %d only" % (self.rank, self.rank))
         plan.gather(self._grads())
-        slot = self.p2p.parity if self.p2p is not None else user   # row of plan.records to write
+        slot = self.p2p.row() if self.p2p is not None else user   # row of plan.records to write
         if self.error_feedback:
             err = self._ef_buffers(user)
             n = plan.arena.numel()
@@ -106,7 +108,7 @@ class PSQuantizer(QuantizerBase):
     def encode_local(self, user, src=None, uniforms=None):
         """Pack one user's gradient (the arena, or `src` laid out like it) into its record.
         Returns the row of plan.records that was written."""
-        slot = self.p2p.parity if self.p2p is not None else user
+        slot = self.p2p.row() if self.p2p is not None else user
         self.plan.encode(slot, src=src, uniforms=uniforms)
         return slot
 
@@ -117,22 +119,27 @@ class PSQuantizer(QuantizerBase):
         plan = self.plan
         out = plan.arena if out is None else out
         if self.p2p is not None:
+            if self.p2p_mode == "push":
+                self.p2p.push()
             self.p2p.barrier()
-            if self.p2p_mode == "direct":
-                g = plan.decode(n_users=self.world, mean=True, out=out, base_ptr=self.p2p.user0_record_ptr(),
-                                user_offsets=self.p2p.user_offsets())
-            else:
-                self.p2p.gather(self._gathered)
-                own = plan.records
-                plan.records = self._gathered
-                try:
-                    g = plan.decode(n_users=self.world, mean=True, out=out)
-                finally:
-                    plan.records = own
+            if self.p2p_mode == "gather":
+                self.p2p.gather()
+            g = self.decode_exchanged(out)
             self.p2p.advance()
             return g
         self.exchange()
         return plan.decode(mean=True, out=out)
+
+    def decode_exchanged(self, out=None):
+        """Decode-and-average all users' records of the current step (after the exchange)."""
+        plan = self.plan
+        out = plan.arena if out is None else out
+        if self.p2p is None:
+            return plan.decode(mean=True, out=out)
+        if self.p2p_mode == "direct":
+            return plan.decode(n_users=self.world, mean=True, out=out, base_ptr=self.p2p.user0_record_ptr(),
+                               user_offsets=self.p2p.user_offsets())
+        return plan.decode(first_user=self.p2p.row(0), n_users=self.world, mean=True, out=out)
 
     # ------------------------------------------------------------------- apply
     def exchange(self):

@@ -246,6 +246,13 @@ int gq_peer_barrier(void *const *flag_ptrs, int rank, int n_ranks, uint32_t epoc
 int gq_peer_gather(void *dst, void *const *src_ptrs, size_t bytes, size_t dst_stride, int n_ranks,
                    gq_stream_t stream);
 
+/* Push variant of the same exchange: before gq_peer_barrier, copy the local record (`bytes`, a
+ * multiple of 16) into each of the n_dst (<= 8) peer-mapped addresses of the HOST array dst_ptrs.
+ * Remote stores are posted, so this is cheaper than pulling; the barrier that follows on the same
+ * stream publishes the data (system-scope release).  Replaces the NCCL all-gather of
+ * quantizers/ps_quantizer.py's exchange, like gq_peer_gather. */
+int gq_peer_push(const void *src, void *const *dst_ptrs, size_t bytes, int n_dst, gq_stream_t stream);
+
 /* ------------------------------------------------------------------------- */
 /* Elementwise helpers the quantizers need around the codecs.
  * out = a + alpha*b  (ps_quantizer.py:35 error feedback; ring_quantizer.py:32)

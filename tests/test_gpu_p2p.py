@@ -67,7 +67,7 @@ def _worker(rank, world, port, out_dir, mode):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["gather", "direct"])
+@pytest.mark.parametrize("mode", ["push", "gather", "direct"])
 def test_ps_peer_to_peer_two_processes_one_gpu(tmp_path, mode):
     world = 2
     mp.start_processes(_worker, args=(world, _free_port(), str(tmp_path), mode), nprocs=world, join=True,
