@@ -270,6 +270,11 @@ def main():
         q.encode_local(rank, src=inputs[i % ROT])              # fused encode into the local packed record
         q.exchange_and_decode(out=outputs[i % ROT])             # P2P barrier (or NCCL all-gather) + fused decode
 
+    # my own kernels per exchange: push/gather + barrier kernel (peer-to-peer); the NCCL all-gather is not mine
+    exchange_launches = 0
+    if q.p2p is not None:
+        exchange_launches = {"push": 2, "gather": 2, "direct": 1}[q.p2p_mode]
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -449,7 +454,7 @@ def main():
                 "api": "PSQuantizer.record(rank)/apply() on gradients copied from pinned host memory each step, "
                        "averaged gradient copied back to pinned host memory each step",
                 "pipelining": "double-buffered: H2D of step i+1 and D2H of step i-1 overlap step i"},
-        "gpu_launches": K * (plan.launches_per_encode() - 1 + plan.launches_per_decode(world)),
+        "gpu_launches": K * (plan.launches_per_encode() + plan.launches_per_decode(world) + exchange_launches),
         "clocks": clocks,
     }
     if not a.no_cpu_baseline:

@@ -39,6 +39,7 @@ _SIGNATURES = {
                                                c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
                                                c_void_p, c_void_p]),
     "gq_f32_reduce_users_scattered": (c_int, [c_void_p, c_void_p, c_int, c_i64, c_int, c_int, c_void_p, c_void_p]),
+    "gq_attach_f32_reduce": (c_int, [c_void_p, c_i64, c_void_p, c_int, c_i64, c_int, c_int, c_void_p]),
     "gq_ipc_alloc": (c_int, [c_size, ctypes.POINTER(c_void_p), c_void_p]),
     "gq_ipc_free": (c_int, [c_void_p]),
     "gq_ipc_open": (c_int, [c_void_p, ctypes.POINTER(c_void_p)]),

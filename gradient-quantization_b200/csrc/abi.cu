@@ -159,6 +159,7 @@ int gq_hsq_encode(const float *grad, int64_t n_chunks, int d, const float *codeb
     }
     GQ_REQUIRE(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
     cudaStream_t st = as_stream(stream);
+    const Rider rider = take_rider();   // attached identity copy, if any: rides in the init kernel
     uint32_t *keys = reinterpret_cast<uint32_t *>(workspace);
     const size_t keys_bytes = align_up((size_t)n_seg * 2 * sizeof(uint32_t), 256);
     uint32_t *barrier = reinterpret_cast<uint32_t *>((char *)workspace + keys_bytes);
@@ -177,13 +178,16 @@ int gq_hsq_encode(const float *grad, int64_t n_chunks, int d, const float *codeb
         GQ_REQUIRE(codes && l && lbub && u_out, "null output pointer");
         GQ_REQUIRE(n_bit <= 7, "uint8 norm codes need n_bit <= 7 (levels 0..2^n)");
         GQ_REQUIRE(((uintptr_t)grad & 15) == 0, "gradient must be 16-byte aligned");
-        e = launch_minmax_init(keys, n_seg, st, barrier);
+        e = launch_minmax_init_rider(keys, n_seg, st, barrier, rider);
         if (e) return e;
         return hsq_encode_tc_fused(grad, n_chunks, codebook, codes, u_out, seg_start, n_seg, keys, barrier, n_bit,
                                    random, uniforms, philox_seed, philox_offset, (uint8_t *)l, lbub, st);
     }
     if (n_bit != 32) {
-        e = launch_minmax_init(keys, n_seg, st);
+        e = launch_minmax_init_rider(keys, n_seg, st, nullptr, rider);
+        if (e) return e;
+    } else {
+        e = launch_rider(rider, st);
         if (e) return e;
     }
     e = gq_hsq_search(grad, n_chunks, d, codebook, K, codes, code_bytes, u_out, seg_start, n_seg,
@@ -215,9 +219,11 @@ int gq_hsq_decode_reduce(const void *codes, int code_bytes, const void *l, int l
     }
     GQ_REQUIRE(n_users == 1 || (user_stride_bytes % 4) == 0, "user stride must be a multiple of 4 bytes");
     GQ_REQUIRE(((uintptr_t)out & 15) == 0, "output must be 16-byte aligned");
-    return hsq_decode_reduce(codes, code_bytes, l, l_bytes, lbub, norms_f32, user_stride_bytes, nullptr, n_users,
-                             n_chunks, d, codebook, K, seg_start, n_seg, n_bit, mean, accumulate, out,
-                             as_stream(stream));
+    e = hsq_decode_reduce(codes, code_bytes, l, l_bytes, lbub, norms_f32, user_stride_bytes, nullptr, n_users,
+                          n_chunks, d, codebook, K, seg_start, n_seg, n_bit, mean, accumulate, out,
+                          as_stream(stream));
+    if (e) return e;
+    return launch_rider(take_rider(), as_stream(stream));   // no-op when the decode kernel carried it
 }
 
 int gq_hsq_decode_reduce_scattered(const void *codes, int code_bytes, const void *l, int l_bytes,
@@ -233,8 +239,10 @@ int gq_hsq_decode_reduce_scattered(const void *codes, int code_bytes, const void
     GQ_REQUIRE(n_bit >= 1 && n_bit <= 24 && l && lbub, "quantized norms required (n_bit 1..24)");
     GQ_REQUIRE(l_bytes == 1 || l_bytes == 4, "l_bytes must be 1 or 4");
     GQ_REQUIRE(((uintptr_t)out & 15) == 0, "output must be 16-byte aligned");
-    return hsq_decode_reduce(codes, code_bytes, l, l_bytes, lbub, nullptr, 0, user_byte_offsets, n_users, n_chunks,
-                             d, codebook, K, seg_start, n_seg, n_bit, mean, accumulate, out, as_stream(stream));
+    e = hsq_decode_reduce(codes, code_bytes, l, l_bytes, lbub, nullptr, 0, user_byte_offsets, n_users, n_chunks,
+                          d, codebook, K, seg_start, n_seg, n_bit, mean, accumulate, out, as_stream(stream));
+    if (e) return e;
+    return launch_rider(take_rider(), as_stream(stream));   // no-op when the decode kernel carried it
 }
 
 int gq_f32_reduce_users(const float *in, int64_t user_stride_bytes, int n_users, int64_t n, int mean,
@@ -252,6 +260,23 @@ int gq_f32_reduce_users_scattered(const float *in, const int64_t *user_byte_offs
     GQ_REQUIRE(n >= 0 && n_users >= 1 && n_users <= 8 && user_byte_offsets, "1..8 users with an offset table");
     GQ_REQUIRE(n == 0 || (in && out), "null pointer");
     return launch_f32_reduce_users(in, 0, user_byte_offsets, n_users, n, mean, accumulate, out, as_stream(stream));
+}
+
+int gq_attach_f32_reduce(const float *in, int64_t user_stride_bytes, const int64_t *user_byte_offsets, int n_users,
+                         int64_t n, int mean, int accumulate, float *out)
+{
+    GQ_REQUIRE(n >= 0 && n_users >= 1 && n_users <= 8, "1..8 users");
+    GQ_REQUIRE(n == 0 || (in && out), "null pointer");
+    Rider r = {};
+    r.in = in;
+    for (int u = 0; u < n_users; ++u) r.off[u] = user_byte_offsets ? user_byte_offsets[u] : (int64_t)u * user_stride_bytes;
+    r.n_users = n_users;
+    r.n = n;
+    r.mean = mean;
+    r.accumulate = accumulate;
+    r.out = out;
+    set_rider(r);
+    return GQ_OK;
 }
 
 int gq_axpy(const float *a, const float *b, float alpha, int64_t n, float *out, gq_stream_t stream)

@@ -6,6 +6,39 @@ namespace gq {
 
 // hsq_exact.cu
 int launch_minmax_init(uint32_t *keys, int n_seg, cudaStream_t st, uint32_t *barrier = nullptr);
+
+// A small fp32 user-reduction (the identity tensors of a model: copy at encode time, sum / mean
+// over users at decode time) that rides inside the first kernel of the next HSQ encode or decode
+// call instead of paying a launch of its own (gq_attach_f32_reduce).  n == 0: none.
+struct Rider {
+    const float *in;
+    int64_t off[8];      // byte offset of user u's data from `in`
+    int n_users;
+    int64_t n;
+    int mean, accumulate;
+    float *out;
+};
+// thread-local pending rider of the calling host thread (n == 0 when none); take_rider() clears it
+Rider take_rider();
+void set_rider(const Rider &r);
+int launch_rider(const Rider &r, cudaStream_t st);   // stand-alone launch (no carrier available)
+__device__ __forceinline__ void rider_run(const Rider &r, int64_t tid, int64_t nthreads)
+{
+    for (int64_t i = tid; i < r.n; i += nthreads) {
+        float acc = 0.0f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (u < r.n_users) {
+                const float x = *reinterpret_cast<const float *>(reinterpret_cast<const char *>(r.in) + r.off[u] + 4 * i);
+                acc = (u == 0) ? x : __fadd_rn(acc, x);
+            }
+        }
+        if (r.mean) acc = __fdiv_rn(acc, (float)r.n_users);
+        if (r.accumulate) acc = __fadd_rn(r.out[i], acc);
+        r.out[i] = acc;
+    }
+}
+int launch_minmax_init_rider(uint32_t *keys, int n_seg, cudaStream_t st, uint32_t *barrier, const Rider &rider);
 int hsq_search_exact(const float *grad, int64_t n_chunks, int d, const float *codebook, int K,
                      void *codes, int code_bytes, float *u_out, const int64_t *seg_start, int n_seg,
                      uint32_t *minmax_keys, cudaStream_t st);

@@ -164,7 +164,7 @@ hsq_search_generic_kernel(const float *__restrict__ grad, int64_t n_chunks, int 
     }
 }
 
-__global__ void minmax_init_kernel(uint32_t *keys, int n_seg, uint32_t *barrier)
+__global__ void minmax_init_kernel(uint32_t *keys, int n_seg, uint32_t *barrier, const Rider rider)
 {
     pdl_launch_dependents();
     pdl_wait();   // the keys may still be read by the previous step's quantize kernel
@@ -174,12 +174,25 @@ __global__ void minmax_init_kernel(uint32_t *keys, int n_seg, uint32_t *barrier)
         keys[2 * i] = GQ_KEY_MIN_INIT;
         keys[2 * i + 1] = GQ_KEY_MAX_INIT;
     }
+    rider_run(rider, i, (int64_t)gridDim.x * blockDim.x);
+}
+
+int launch_minmax_init_rider(uint32_t *keys, int n_seg, cudaStream_t st, uint32_t *barrier, const Rider &rider)
+{
+    int64_t blocks = (n_seg + 127) / 128;
+    const int64_t rb = (rider.n + 127) / 128;
+    if (rb > blocks) blocks = rb;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    GQ_CUDA(launch_pdl(minmax_init_kernel, dim3((unsigned)blocks), dim3(128), 0, st, keys, n_seg, barrier, rider));
+    return GQ_OK;
 }
 
 int launch_minmax_init(uint32_t *keys, int n_seg, cudaStream_t st, uint32_t *barrier)
 {
-    GQ_CUDA(launch_pdl(minmax_init_kernel, dim3((n_seg + 127) / 128), dim3(128), 0, st, keys, n_seg, barrier));
-    return GQ_OK;
+    Rider none = {};
+    return launch_minmax_init_rider(keys, n_seg, st, barrier, none);
 }
 
 template <int D, typename CodeT>

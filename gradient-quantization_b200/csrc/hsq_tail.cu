@@ -552,7 +552,7 @@ hsq_decode_reduce_staged_kernel(const uint8_t *__restrict__ codes, const uint8_t
                                 const float *__restrict__ lbub, const UserOffsets uoff,
                                 int64_t n_chunks, const float *__restrict__ codebook,
                                 const int64_t *__restrict__ seg_start, int n_seg, float s, int mean,
-                                int accumulate, float *__restrict__ out)
+                                int accumulate, float *__restrict__ out, const Rider rider)
 {
     extern __shared__ float4 s_dyn[];
     float4 *s_cb = s_dyn;                                                    // [256][2][4]
@@ -605,6 +605,8 @@ hsq_decode_reduce_staged_kernel(const uint8_t *__restrict__ codes, const uint8_t
     int64_t tile = blockIdx.x;
     int buf = 0;
     if (tile < n_tiles) issue(tile, 0);
+    // the attached small reduction (identity tensors) runs while the first tile is in flight
+    rider_run(rider, (int64_t)blockIdx.x * kDecodeThreads + tid, (int64_t)gridDim.x * kDecodeThreads);
     for (; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
         const int64_t next = tile + gridDim.x;
         if (next < n_tiles) {
@@ -694,9 +696,10 @@ static int launch_decode_staged(const void *codes, const void *l, const float *l
     const int64_t per = (n_tiles + cap - 1) / cap;
     int64_t grid = (n_tiles + per - 1) / per;
     if (grid < 1) grid = 1;
+    const Rider rider = take_rider();   // carried by this launch if one is pending
     GQ_CUDA(launch_pdl(kern, dim3((unsigned)grid), dim3(kDecodeThreads), smem, st, (const uint8_t *)codes,
                        (const uint8_t *)l, lbub, uoff, n_chunks, codebook, seg_start, n_seg, s, mean,
-                       accumulate, out));
+                       accumulate, out, rider));
     return GQ_OK;
 }
 
@@ -879,6 +882,32 @@ int launch_f32_reduce_users(const float *in, int64_t user_stride, const int64_t 
     }
     GQ_CUDA(launch_pdl(f32_reduce_users_kernel, dim3(grid_for(n, 256)), dim3(256), 0, st, in, user_stride, n_users,
                        n, mean, accumulate, out));
+    return GQ_OK;
+}
+
+// ---------------------------------------------------------- attached reduction ---
+static thread_local Rider g_rider = {};
+
+void set_rider(const Rider &r) { g_rider = r; }
+
+Rider take_rider()
+{
+    Rider r = g_rider;
+    g_rider = Rider{};
+    return r;
+}
+
+__global__ void __launch_bounds__(256) rider_kernel(const Rider rider)
+{
+    pdl_launch_dependents();
+    pdl_wait();
+    rider_run(rider, (int64_t)blockIdx.x * 256 + threadIdx.x, (int64_t)gridDim.x * 256);
+}
+
+int launch_rider(const Rider &r, cudaStream_t st)
+{
+    if (r.n == 0) return GQ_OK;
+    GQ_CUDA(launch_pdl(rider_kernel, dim3(grid_for(r.n, 256)), dim3(256), 0, st, r));
     return GQ_OK;
 }
 

@@ -355,7 +355,7 @@ hsq_search_tc_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_
             // pass over the 256 approximate scores of this row: max |.| per group of 4 codewords
             float gm[kNumGroups];
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * kK);
-            if (!kDebug) {
+            if (!kDebug || dbg_tiles == 0) {   // (debug builds keep it unless they dump the scores)
                 // software-pipelined: the load of the next 16 columns is in flight while the
                 // previous 16 are reduced (two 16-register buffers); 60 vs 64 us on B200
                 uint32_t sa[16], sb[16];

@@ -207,6 +207,17 @@ class FusedPlan:
     def views(self, buf=None):
         return [self.view(i, buf) for i in range(len(self.sizes))]
 
+    def locate(self, tensors):
+        """If the tensors are views of ONE buffer laid out like the arena (e.g. made with views(buf)),
+        return that buffer's base address (encode can read it in place); else None."""
+        if len(tensors) != len(self.sizes) or not tensors:
+            return None
+        base = tensors[0].data_ptr() - self.tensor_off[0] * 4
+        for t, o in zip(tensors, self.tensor_off):
+            if t.data_ptr() != base + o * 4 or t.dtype != torch.float32 or not t.is_contiguous():
+                return None
+        return base if base % 256 == 0 else None
+
     def gather(self, tensors, buf=None):
         """Copy per-parameter gradients into the arena (skips views already in it)."""
         dst, src = [], []
@@ -270,14 +281,21 @@ class FusedPlan:
     # --------------------------------------------------------------- encode ---
     def encode(self, user, src=None, uniforms=None):
         """Compress the arena (or `src`, laid out like it) into records[user].
-        Launches: HSQ 3 per group (init, search, quantize), QSGD 3, sign 1, top-k 12, identity 1."""
+        Launches: HSQ 3 per group (init, search, quantize), QSGD 3, sign 1, top-k 12; the copy of
+        the identity tensors rides in the first HSQ group's init kernel (1 launch of its own
+        when there is no HSQ group)."""
         src = self.arena if src is None else src
+        src_ptr = src if isinstance(src, int) else src.data_ptr()   # tensor or raw device address
         rec = self.records[user]
         st = _lib.stream()
         base = rec.data_ptr()
+        ident, carrier = self._rider_pair()
         for g in self.groups:
-            gp = src.data_ptr() + g.arena_off * 4
+            gp = src_ptr + g.arena_off * 4
             r = None if uniforms is None else uniforms.get(id(g))
+            if g is carrier:   # out = the raw fp32 tensors, copied into the record by the next call
+                _lib.call("gq_attach_f32_reduce", src_ptr + ident.arena_off * 4, 0, None, 1, ident.n, 0, 0,
+                          base + ident.raw_off)
             if g.kind == "hsq":
                 n_rand = g.n_chunks if (self.random and g.n_bit != 32) else 0
                 seed, off = _lib.PHILOX.take(n_rand) if (n_rand and r is None) else (0, 0)
@@ -304,8 +322,17 @@ class FusedPlan:
                           _lib.ptr(g.k_prefix), g.n_seg, None, base + g.idx_off, base + g.val_off,
                           _lib.ptr(self.workspace), self.workspace.numel(), st)
             elif g.kind == "identity":
-                if g.n:   # out = a + 0 * b: a plain copy of the raw fp32 tensors into the record
+                if g.n and carrier is None:   # a plain copy of the raw fp32 tensors into the record
                     _lib.call("gq_f32_reduce_users", gp, 0, 1, g.n, 0, 0, base + g.raw_off, st)
+
+    def _rider_pair(self, n_users=1):
+        """(identity group, HSQ group whose first kernel carries the identity tensors' copy /
+        reduction) or (None, None)."""
+        ident = next((g for g in self.groups if g.kind == "identity" and g.n), None)
+        carrier = next((g for g in self.groups if g.kind == "hsq"), None)
+        if ident is None or carrier is None or n_users > 8:
+            return None, None
+        return ident, carrier
 
     # --------------------------------------------------------------- decode ---
     def supports_scattered(self):
@@ -328,15 +355,19 @@ class FusedPlan:
         st = _lib.stream()
         mean = 1 if mean else 0
         acc = 1 if accumulate else 0
+        ident, carrier = self._rider_pair(n_users)
         if user_offsets is not None:
             for g in self.groups:
                 op = out.data_ptr() + g.arena_off * 4
+                if g is carrier:
+                    _lib.call("gq_attach_f32_reduce", base_ptr + ident.raw_off, 0, user_offsets, n_users, ident.n,
+                              mean, acc, out.data_ptr() + ident.arena_off * 4)
                 if g.kind == "hsq":
                     _lib.call("gq_hsq_decode_reduce_scattered", base_ptr + g.codes_off, g.code_bytes,
                               base_ptr + g.l_off, g.l_bytes, base_ptr + g.lbub_off, user_offsets, n_users,
                               g.n_chunks, g.dim, _lib.ptr(g.codebook), g.K, _lib.ptr(g.seg_start), g.n_seg,
                               g.n_bit, mean, acc, op, st)
-                else:
+                elif carrier is None:
                     _lib.call("gq_f32_reduce_users_scattered", base_ptr + g.raw_off, user_offsets, n_users, g.n,
                               mean, acc, op, st)
             return out
@@ -344,6 +375,9 @@ class FusedPlan:
         stride = self.record_bytes
         for g in self.groups:
             op = out.data_ptr() + g.arena_off * 4
+            if g is carrier:
+                _lib.call("gq_attach_f32_reduce", base + ident.raw_off, stride, None, n_users, ident.n, mean, acc,
+                          out.data_ptr() + ident.arena_off * 4)
             if g.kind == "hsq":
                 if g.n_bit == 32:
                     _lib.call("gq_hsq_decode_reduce", base + g.codes_off, g.code_bytes, None, 1, None,
@@ -363,16 +397,24 @@ class FusedPlan:
             elif g.kind == "topk":
                 _lib.call("gq_topk_scatter_reduce", base + g.idx_off, base + g.val_off, stride, n_users,
                           g.k_total, g.n, mean, acc, op, st)
-            elif g.kind == "identity":
+            elif g.kind == "identity" and carrier is None:
                 _lib.call("gq_f32_reduce_users", base + g.raw_off, stride, n_users, g.n, mean, acc, op, st)
         return out
 
     def launches_per_encode(self):
         per = {"hsq": 3, "qsgd": 3, "sign": 1, "topk": 12, "identity": 1}
-        return sum(per[g.kind] - (1 if (g.kind == "hsq" and g.n_bit == 32) else 0) for g in self.groups)
+        n = sum(per[g.kind] - (1 if (g.kind == "hsq" and g.n_bit == 32) else 0) for g in self.groups)
+        ident, carrier = self._rider_pair()
+        if carrier is not None and carrier.n_bit != 32:   # the copy rides in the HSQ init kernel
+            n -= 1
+        return n
 
     def launches_per_decode(self, n_users):
         n = 0
         for g in self.groups:
             n += (2 + n_users) if g.kind == "topk" else 1
+        ident, carrier = self._rider_pair(n_users)
+        if (carrier is not None and carrier.dim == 16 and carrier.K == 256 and carrier.code_bytes == 1
+                and carrier.l_bytes == 1 and carrier.n_bit != 32):   # rides in the staged decode kernel
+            n -= 1
         return n

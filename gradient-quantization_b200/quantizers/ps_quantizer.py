@@ -70,8 +70,14 @@ class PSQuantizer(QuantizerBase):
         plan = self.plan
         if self.distributed and user != self.rank:
             raise _lib.GQError("distributed mode: rank %d records user %d only" % (self.rank, self.rank))
-        plan.gather(self._grads())
         slot = self.p2p.row() if self.p2p is not None else user   # row of plan.records to write
+        grads = self._grads()
+        if not self.error_feedback:
+            flat = plan.locate(grads)
+            if flat is not None:          # gradients already form one arena-shaped buffer: read in place
+                plan.encode(slot, src=flat, uniforms=uniforms)
+                return
+        plan.gather(grads)
         if self.error_feedback:
             err = self._ef_buffers(user)
             n = plan.arena.numel()

@@ -148,6 +148,16 @@ int gq_hsq_decode_reduce_scattered(const void *codes, int code_bytes, const void
 int gq_f32_reduce_users_scattered(const float *in, const int64_t *user_byte_offsets, int n_users, int64_t n,
                                   int mean, int accumulate, float *out, gq_stream_t stream);
 
+/* Attach a small gq_f32_reduce_users[_scattered] job (the identity tensors of a model: n_users = 1
+ * copy at encode time, sum / mean over users at decode time) to the NEXT gq_hsq_encode,
+ * gq_hsq_decode_reduce or gq_hsq_decode_reduce_scattered call made by this host thread: it runs
+ * inside that call's first kernel (or, if that code path cannot carry it, in a launch of its own
+ * issued by that call) instead of costing a separate ~3 us launch.  Same arguments and results as
+ * gq_f32_reduce_users (user_byte_offsets == NULL: user u at in + u * user_stride_bytes) /
+ * gq_f32_reduce_users_scattered.  n_users <= 8.  The job is dropped if no such call follows. */
+int gq_attach_f32_reduce(const float *in, int64_t user_stride_bytes, const int64_t *user_byte_offsets,
+                         int n_users, int64_t n, int mean, int accumulate, float *out);
+
 /* out[i] = (sum_u in[u*user_stride_bytes + 4*i]) / U (mean) -- identity tensors
  * (compressors/identical_compressor.py:5-11 under ps_quantizer.py:48). */
 int gq_f32_reduce_users(const float *in, int64_t user_stride_bytes, int n_users, int64_t n,

@@ -13,12 +13,12 @@ n_chunks = 1468652
 x = torch.randn(n_chunks * 16, device=dev) * 0.01
 codes = torch.empty(n_chunks, dtype=torch.uint8, device=dev); u = torch.empty(n_chunks, device=dev)
 seg = torch.tensor([0, n_chunks], dtype=torch.int64, device=dev)
-dbg = torch.zeros(128 * 256 + n_chunks * 24 + 2 * 6 * 128 + 16, device=dev)
+dbg = torch.zeros(n_chunks * 24 + 2 * 6 * 128 + 16, device=dev)
 for _ in range(2):
     _lib.call("gq_hsq_tc_debug", x.data_ptr(), n_chunks, cbt.data_ptr(), codes.data_ptr(), u.data_ptr(),
-              seg.data_ptr(), 1, dbg.data_ptr(), 1, _lib.stream())
+              seg.data_ptr(), 1, dbg.data_ptr(), 0, _lib.stream())
 torch.cuda.synchronize()
-tr = dbg[128 * 256 + n_chunks * 24: 128 * 256 + n_chunks * 24 + 2 * 6 * 128].cpu().numpy().view(np.int64).reshape(6, 128)
+tr = dbg[n_chunks * 24: n_chunks * 24 + 2 * 6 * 128].cpu().numpy().view(np.int64).reshape(6, 128)
 t0 = tr[0, 0]
 names = ["TMA issued", "MMA issued", "acc seen", "TMEM released", "stage released", "tile done"]
 print("it  " + "  ".join("%14s" % n for n in names) + "   (cycles since first TMA issue; debug build)")
