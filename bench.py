@@ -444,7 +444,8 @@ def main():
                    "elements_per_user": n_total, "compressed_elements": plan.compressed_elems(),
                    "users": world, "wire_bytes_per_user": plan.wire_bytes(), "algo": a.algo,
                    "exchange": ("none (1 user)" if world == 1 else
-                                ("peer-to-peer (%s): packed records cross NVLink through peer-mapped memory, barrier kernel" % q.p2p_mode
+                                ("peer-to-peer (%s%s): packed records cross NVLink through peer-mapped memory, barrier kernel"
+                                 % (q.p2p_mode, ", NVLS multicast stores" if (q.p2p_mode == "push" and q.p2p.mc_base) else "")
                                  if q.p2p is not None else "NCCL all-gather of packed records")),
                    "l2": "inputs/outputs rotate over %d buffers of %.0f MB each (> 126 MB L2)"
                          % (ROT, plan.arena_elems * 4 / 1e6)},

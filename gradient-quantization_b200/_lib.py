@@ -47,6 +47,7 @@ _SIGNATURES = {
     "gq_peer_barrier": (c_int, [c_void_p, c_int, c_int, ctypes.c_uint32, c_void_p]),
     "gq_peer_gather": (c_int, [c_void_p, c_void_p, c_size, c_size, c_int, c_void_p]),
     "gq_peer_push": (c_int, [c_void_p, c_void_p, c_size, c_int, c_void_p]),
+    "gq_peer_push_multicast": (c_int, [c_void_p, c_void_p, c_size, c_void_p]),
     "gq_f32_reduce_users": (c_int, [c_void_p, c_i64, c_int, c_i64, c_int, c_int, c_void_p, c_void_p]),
     "gq_qsgd_wire_bits": (c_int, [c_int]),
     "gq_qsgd_encode": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_int, c_int, c_int, c_void_p, c_u64,

@@ -87,6 +87,23 @@ peer_push_kernel(const uint4 *__restrict__ src, const PeerDst dst, int n_dst, si
         for (int d = 0; d < 8; ++d)
             if (d < n_dst) dst.p[d][i] = a;
     }
+    __threadfence_system();
+}
+
+// the same push through an NVSwitch multicast mapping (NVLS): ONE multimem store per 16 bytes is
+// replicated by the switch into every rank's buffer, so the sender's NVLink egress is one record
+// instead of (ranks - 1) records
+__global__ void __launch_bounds__(256)
+peer_push_mc_kernel(const uint4 *__restrict__ src, uint4 *mc_dst, size_t n16)
+{
+    const size_t step = (size_t)gridDim.x * 256;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n16; i += step) {
+        const uint4 a = src[i];
+        asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                     ::"l"(mc_dst + i), "f"(__uint_as_float(a.x)), "f"(__uint_as_float(a.y)),
+                       "f"(__uint_as_float(a.z)), "f"(__uint_as_float(a.w)) : "memory");
+    }
+    __threadfence_system();
 }
 
 }  // namespace gq
@@ -182,6 +199,24 @@ int gq_peer_push(const void *src, void *const *dst_ptrs, size_t bytes, int n_dst
     if (bx < 1) bx = 1;
     peer_push_kernel<<<bx, 256, 0, as_stream(stream)>>>(reinterpret_cast<const uint4 *>(src), pd, n_dst, n16);
     GQ_LAUNCH_CHECK("peer_push");
+    return GQ_OK;
+}
+
+// Multicast variant: mc_dst is the address of the destination row inside an NVSwitch multicast
+// mapping of the ranks' (symmetric) buffers, e.g. torch symmetric memory's multicast_ptr + offset.
+int gq_peer_push_multicast(const void *src, void *mc_dst, size_t bytes, gq_stream_t stream)
+{
+    GQ_REQUIRE(src && mc_dst, "bad arguments");
+    GQ_REQUIRE(bytes % 16 == 0 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)mc_dst & 15) == 0, "16-byte granularity");
+    if (bytes == 0) return GQ_OK;
+    const size_t n16 = bytes / 16;
+    int bx = (int)((n16 + 255) / 256);
+    const int cap = sm_count() * 4;
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    peer_push_mc_kernel<<<bx, 256, 0, as_stream(stream)>>>(reinterpret_cast<const uint4 *>(src),
+                                                           reinterpret_cast<uint4 *>(mc_dst), n16);
+    GQ_LAUNCH_CHECK("peer_push_multicast");
     return GQ_OK;
 }
 

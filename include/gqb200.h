@@ -263,6 +263,11 @@ int gq_peer_gather(void *dst, void *const *src_ptrs, size_t bytes, size_t dst_st
  * quantizers/ps_quantizer.py's exchange, like gq_peer_gather. */
 int gq_peer_push(const void *src, void *const *dst_ptrs, size_t bytes, int n_dst, gq_stream_t stream);
 
+/* The same push through an NVSwitch multicast (NVLS) mapping of the ranks' symmetric buffers:
+ * mc_dst = multicast address of the destination row (identical offset in every rank's buffer).
+ * One multimem.st per 16 bytes is replicated by the switch to every rank (the sender included). */
+int gq_peer_push_multicast(const void *src, void *mc_dst, size_t bytes, gq_stream_t stream);
+
 /* ------------------------------------------------------------------------- */
 /* Elementwise helpers the quantizers need around the codecs.
  * out = a + alpha*b  (ps_quantizer.py:35 error feedback; ring_quantizer.py:32)

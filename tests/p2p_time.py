@@ -24,6 +24,8 @@ q = gq_b200.Quantizer(gq_b200.NearestNeighborCompressor, params, a)
 assert q.p2p is not None
 plan, p2p = q.plan, q.p2p
 out = torch.empty_like(plan.arena)
+if rank == 0:
+    print("alloc=%s multicast=%s" % (p2p.alloc, bool(p2p.mc_base)), flush=True)
 for row in range(2 * world):          # fill every row of the local block
     plan.arena.normal_(0, 0.01)
     plan.encode(row)

@@ -29,6 +29,7 @@ def _worker(rank, world, port, out_dir, mode):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     os.environ["GQ_P2P_MODE"] = mode
+    os.environ["GQ_P2P_ALLOC"] = "ipc"     # two ranks on ONE device: CUDA IPC (symmetric memory / NVLS need one GPU per rank)
     import torch.distributed as dist
     torch.cuda.set_device(0)
     dist.init_process_group("gloo", rank=rank, world_size=world)
