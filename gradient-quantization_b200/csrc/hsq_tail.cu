@@ -58,47 +58,70 @@ norm_quantize_kernel(const float *__restrict__ u, int64_t n, const int64_t *__re
                               n_seg, s, random, uniforms, seed, offset, l, keys);
 }
 
-// Same, with the segment table and the decoded lb/ub staged in shared memory: the kernel is a
-// single wave whose run time is one chain of dependent loads per thread, and the 7-step binary
-// search over global memory was the longest link of that chain.
+// Same, instruction-lean (the kernel is issue-bound, not HBM-bound: 5.6 M warp instructions for
+// 7 MB of traffic in its first version): 32-bit segment table and decoded (lb, ub) pairs in shared
+// memory; the segment of a block's first chunk is COUNTED by the block (one __syncthreads_count
+// per 256 segments) instead of binary-searched per thread; four consecutive chunks per thread =
+// one float4 of u (and of the uniforms), one Philox4x32-10 block, one packed store; when all four
+// lie in one tensor (almost always) lb, ub and ub - lb are fetched once.  The host sizes the grid
+// so that it is ONE resident wave with `items` groups per thread, a grid-width apart (1435 blocks
+// of one item each were 1.2 waves on 148 SMs: the second, nearly empty wave doubled the run
+// time); the loads of the next item are issued before the current one is processed.
 constexpr int kQuantMaxSeg = 1024;
+__device__ __forceinline__ int psc_level_nz(float v, float lb, float den, float s, int random, float r)
+{
+    // psc_level() for lb != ub, with den = ub - lb computed by the caller (same operations)
+    const float scaled = fabsf(__fdiv_rn(__fsub_rn(v, lb), den)) * s;
+    const float c = fminf(fmaxf(scaled, 0.0f), s - 1.0f);
+    int li = (int)c;
+    if (random) li += (__fsub_rn(scaled, (float)li) > r) ? 1 : 0;
+    return li;
+}
 template <typename LT>
 __global__ void __launch_bounds__(256)
-norm_quantize_smem_kernel(const float *__restrict__ u, int64_t n, const int64_t *__restrict__ seg_start,
+norm_quantize_smem_kernel(const float *__restrict__ u, int n, const int64_t *__restrict__ seg_start,
                           int n_seg, float s, int random, const float *__restrict__ uniforms,
                           uint64_t seed, uint64_t offset, LT *__restrict__ l, float *__restrict__ lbub,
-                          const uint32_t *__restrict__ keys)
+                          const uint32_t *__restrict__ keys, int items)
 {
-    extern __shared__ int64_t s_seg[];                                   // [n_seg + 1]
-    float *s_lbub = reinterpret_cast<float *>(s_seg + n_seg + 1);       // [2 * n_seg]
+    extern __shared__ int s_segi[];                                                  // [n_seg + 1]
+    float2 *s_lbub2 = reinterpret_cast<float2 *>(s_segi + ((n_seg + 2) & ~1));      // [n_seg]
+    const int tid = threadIdx.x;
     pdl_launch_dependents();
-    for (int i = threadIdx.x; i <= n_seg; i += 256) s_seg[i] = seg_start[i];
+    for (int i = tid; i <= n_seg; i += 256) s_segi[i] = (int)seg_start[i];
     pdl_wait();   // keys and u come from the search kernel
-    for (int i = threadIdx.x; i < 2 * n_seg; i += 256) {
-        const float f = key_to_float(keys[i]);
-        s_lbub[i] = f;
-        if (blockIdx.x == 0) lbub[i] = f;
+    for (int i = tid; i < n_seg; i += 256) {
+        const float lb = key_to_float(keys[2 * i]), ub = key_to_float(keys[2 * i + 1]);
+        s_lbub2[i] = make_float2(lb, ub);
+        if (blockIdx.x == 0) {   // the reference returns lb/ub (probabilistic_scalar_compressor.py:27)
+            lbub[2 * i] = lb;
+            lbub[2 * i + 1] = ub;
+        }
     }
-    // Each thread handles groups of four chunks a grid-width apart (coalesced); the host sizes the
-    // grid so that it is ONE resident wave with the items spread evenly (1435 blocks of one item
-    // each were 1.2 waves on 148 SMs: the second, nearly empty wave doubled the run time).  The
-    // loads of the next item are issued before the current one is processed.
-    const int64_t n4 = (n + 3) / 4;
-    const int64_t stride = (int64_t)gridDim.x * 256;
-    int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int n4 = (n + 3) >> 2;
+    const int stride = gridDim.x * 256;
+    int q = blockIdx.x * 256 + tid;
     float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), rv = make_float4(0.f, 0.f, 0.f, 0.f);
     if (q < n4 && q * 4 + 3 < n) {
         xv = __ldg(reinterpret_cast<const float4 *>(u) + q);
         if (random && uniforms) rv = __ldg(reinterpret_cast<const float4 *>(uniforms) + q);
     }
+    const bool philox = random && !uniforms;
+    const bool philox_aligned = (offset & 3u) == 0;
     __syncthreads();
-    for (; q < n4; q += stride) {
+    for (int it = 0; it < items; ++it, q += stride) {   // uniform trip count (block-wide barriers inside)
+        // segment holding the first chunk of this block's range
+        const int block_i0 = (blockIdx.x * 256 + it * stride) * 4;
+        int base = -1;
+        for (int j0 = 0; j0 < n_seg; j0 += 256)
+            base += __syncthreads_count(j0 + tid < n_seg && s_segi[j0 + tid] <= block_i0);
+        if (q >= n4) continue;
         const bool full = q * 4 + 3 < n;
-        const int64_t i0 = q * 4;
+        const int i0 = q * 4;
         float x[4] = {xv.x, xv.y, xv.z, xv.w}, r[4] = {rv.x, rv.y, rv.z, rv.w};
         {
-            const int64_t qn = q + stride;
-            if (qn < n4 && qn * 4 + 3 < n) {
+            const int qn = q + stride;
+            if (it + 1 < items && qn < n4 && qn * 4 + 3 < n) {
                 xv = __ldg(reinterpret_cast<const float4 *>(u) + qn);
                 if (random && uniforms) rv = __ldg(reinterpret_cast<const float4 *>(uniforms) + qn);
             }
@@ -110,8 +133,8 @@ norm_quantize_smem_kernel(const float *__restrict__ u, int64_t n, const int64_t 
                 r[t] = (random && uniforms && i0 + t < n) ? uniforms[i0 + t] : 0.0f;
             }
         }
-        if (random && !uniforms) {
-            if (((offset + (uint64_t)i0) & 3u) == 0) {
+        if (philox) {
+            if (philox_aligned) {
                 const uint4 w = philox4x32_10(seed, (offset + (uint64_t)i0) >> 2);
                 r[0] = u01(w.x); r[1] = u01(w.y); r[2] = u01(w.z); r[3] = u01(w.w);
             } else {
@@ -119,25 +142,29 @@ norm_quantize_smem_kernel(const float *__restrict__ u, int64_t n, const int64_t 
                 for (int t = 0; t < 4; ++t) r[t] = philox_uniform(seed, offset, (uint64_t)(i0 + t));
             }
         }
-        // segment of the first chunk by binary search in shared memory, then walk forward
-        int seg = 0;
-        {
-            int lo = 0, hi = n_seg;
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (s_seg[mid] <= i0) lo = mid; else hi = mid;
-            }
-            seg = lo;
-        }
+        int seg = base < 0 ? 0 : base;
+        while (i0 >= s_segi[seg + 1]) ++seg;
         int lv[4];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const int64_t i = i0 + t;
-            if (i < n) {
-                while (i >= s_seg[seg + 1]) ++seg;
-                lv[t] = psc_level(x[t], s_lbub[2 * seg], s_lbub[2 * seg + 1], s, random, r[t]);
+        if (i0 + 3 < s_segi[seg + 1]) {   // all four chunks in one tensor
+            const float2 b = s_lbub2[seg];
+            if (b.x - b.y == 0.0f) {
+                lv[0] = lv[1] = lv[2] = lv[3] = 0;
             } else {
-                lv[t] = 0;
+                const float den = __fsub_rn(b.y, b.x);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) lv[t] = psc_level_nz(x[t], b.x, den, s, random, r[t]);
+            }
+        } else {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int i = i0 + t;
+                if (i < n) {
+                    while (i >= s_segi[seg + 1]) ++seg;
+                    const float2 b = s_lbub2[seg];
+                    lv[t] = psc_level(x[t], b.x, b.y, s, random, r[t]);
+                } else {
+                    lv[t] = 0;
+                }
             }
         }
         if (full) {
@@ -194,9 +221,9 @@ int launch_norm_quantize(const float *u, int64_t n, const int64_t *seg_start, in
     const int64_t n4 = (n + 3) / 4;
     const bool aligned = (((uintptr_t)u & 15) == 0) && (uniforms == nullptr || ((uintptr_t)uniforms & 15) == 0) &&
                          (((uintptr_t)l & (4 * (size_t)l_bytes - 1)) == 0);
-    if (n_seg <= kQuantMaxSeg && aligned && n4 > 0 && n4 < ((int64_t)1 << 31) * 256) {
-        // one thread per four chunks, tables in shared memory
-        const size_t smem = (size_t)(n_seg + 1) * 8 + (size_t)n_seg * 8;
+    if (n_seg <= kQuantMaxSeg && aligned && n4 > 0 && n < ((int64_t)1 << 31) - 8) {
+        // tables in shared memory, 32-bit indices
+        const size_t smem = (size_t)((n_seg + 2) & ~1) * 4 + (size_t)n_seg * 8;
         const int64_t blocks = (n4 + 255) / 256;
         int occ = 1;
         if (l_bytes == 1)
@@ -204,14 +231,14 @@ int launch_norm_quantize(const float *u, int64_t n, const int64_t *seg_start, in
         else
             GQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, norm_quantize_smem_kernel<int32_t>, 256, smem));
         const int64_t cap = (int64_t)sm_count() * (occ < 1 ? 1 : occ);
-        const int64_t items = (blocks + cap - 1) / cap;                    // per thread
+        const int items = (int)((blocks + cap - 1) / cap);                 // per thread
         const unsigned grid = (unsigned)((blocks + items - 1) / items);    // one wave, evenly loaded
         if (l_bytes == 1)
-            GQ_CUDA(launch_pdl(norm_quantize_smem_kernel<uint8_t>, dim3(grid), dim3(256), smem, st, u, n, seg_start,
-                               n_seg, s, random, uniforms, seed, offset, (uint8_t *)l, lbub, keys));
+            GQ_CUDA(launch_pdl(norm_quantize_smem_kernel<uint8_t>, dim3(grid), dim3(256), smem, st, u, (int)n, seg_start,
+                               n_seg, s, random, uniforms, seed, offset, (uint8_t *)l, lbub, keys, items));
         else
-            GQ_CUDA(launch_pdl(norm_quantize_smem_kernel<int32_t>, dim3(grid), dim3(256), smem, st, u, n, seg_start,
-                               n_seg, s, random, uniforms, seed, offset, (int32_t *)l, lbub, keys));
+            GQ_CUDA(launch_pdl(norm_quantize_smem_kernel<int32_t>, dim3(grid), dim3(256), smem, st, u, (int)n, seg_start,
+                               n_seg, s, random, uniforms, seed, offset, (int32_t *)l, lbub, keys, items));
         return GQ_OK;
     }
     const int grid = grid_for(n > 0 ? n4 : 1, 256);
