@@ -3,21 +3,21 @@
 //
 // Per 128-chunk tile the [128 x 16] x [16 x 256] inner-product contraction of
 // nearest_neighbor_compressor.py:68 runs on the 5th-gen tensor cores:
-//   TMA  : gradient tile (8 KB, row = chunk = 64 B, SWIZZLE_64B) -> smem ring;
-//          codebook (16 KB) -> smem once per CTA
+//   TMA  : gradient tile (8 KB, row = chunk = 64 B, SWIZZLE_64B) -> 6-stage smem ring.
+//          The codebook operand (16 KB, rounded to nearest TF32) and four exact, bank-conflict-free
+//          "planes" of the codebook for rescoring (128 KB) are written once per CTA.
 //   MMA  : 2 x tcgen05.mma kind::tf32 (M=128, N=256, K=8), fp32 accumulators in
 //          TMEM, two 256-column buffers so the next tile's MMA overlaps the epilogue
-//   EPI  : each of the 128 rows is one thread: tcgen05.ld its 256 approximate
-//          scores, keep only max|.| per group of 8 codewords (never touches HBM),
-//          then RESCORE in exact fp32 every codeword of every group whose maximum
-//          lies within 2*eps of the row maximum.
+//   EPI  : three groups of four warps take tiles round-robin; each of the 128 rows is one thread:
+//          software-pipelined tcgen05.ld of its 256 approximate scores, of which only max|.| per
+//          group of 4 codewords is kept (the scores never touch HBM), then it RESCORES in exact
+//          fp32 every codeword of every group whose maximum lies within 2*eps of the row maximum.
 // Bit-exactness argument: |approx_k - exact_k| <= eps(v) for all k  =>  the exact
 // argmax (and every exact tie) has approx >= max_approx - 2 eps, so it is inside
 // the rescored set; the rescoring is the same ascending-j FMA chain and the same
 // "first index wins" rule as hsq_exact.cu, hence identical codes and u.
-// eps(v) = 1.5 * 2^-9 * ||v||_2 covers TF32 operand truncation (2^-10 relative per
-// operand, unit-norm codewords, Cauchy-Schwarz) with a 1.5x safety factor; rows
-// with a non-finite norm rescore all 256 codewords.
+// eps(v) = (1.5 * 2^-10 + 4e-6) * ||v||_2 * max_k ||c_k||_2 -- see kMargin; rows with a non-finite
+// or vanishing norm rescore all 256 codewords (all-zero rows: codeword 0).
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -43,11 +43,12 @@ constexpr uint32_t kPlaneBytes = kK * 128;        // one rescoring plane: 128-by
 constexpr int kPlanes = 4;
 // Rescoring margin, 2 * eps / (||v|| max_k ||c_k||).  The tensor core reads the top 19 bits of an
 // fp32 operand (TF32, truncation -- measured: adding the two truncation remainders back with extra
-// MMAs leaves a residual of 1.1e-6 ||v||), so every product is off by at most 2^-9 |v_j c_kj|
-// whatever the rounding of either operand, the sum by at most 2^-9 ||v|| ||c_k|| (Cauchy-Schwarz);
-// the fp32 accumulation of 16 terms adds < 16 * 2^-23 ||v|| ||c_k||; 4e-6 covers that, the
-// rounding of ||v|| and of the threshold itself.  Largest error measured: 1.15e-3 ||v||.
-constexpr float kMargin = 2.0f * (1.0f / 512.0f + 4.0e-6f);
+// MMAs leaves a residual of 1.1e-6 ||v||): the gradient operand is therefore off by < 2^-10 |v_j|.
+// The codebook operand is rounded to nearest TF32 in shared memory once per CTA (cvt.rna), off by
+// <= 2^-11 |c_kj|.  Every product is thus within (2^-10 + 2^-11 + 2^-21) |v_j c_kj|, the sum within
+// 1.5 * 2^-10 ||v|| ||c_k|| (Cauchy-Schwarz); the fp32 accumulation of 16 terms adds
+// < 16 * 2^-23 ||v|| ||c_k||; 4e-6 covers that, the rounding of ||v|| and of the threshold itself.
+constexpr float kMargin = 2.0f * (1.5f / 1024.0f + 4.0e-6f);
 
 static_assert(kStages % 2 == 0 && kStages % 3 == 0, "barrier ring must be a multiple of the buffer and group counts");
 constexpr uint32_t kOffA = 0;
@@ -226,9 +227,9 @@ hsq_search_tc_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_
     const uint32_t bar_tfull = bar_empty + 8 * kStages;
     const uint32_t bar_tempty = bar_tfull + 8 * kStages;
     const uint32_t bar_cb = bar_tempty + 8 * kStages;
-    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(smem + kOffBar + 8 * (4 * kStages + 1));
-    float *s_cn2 = reinterpret_cast<float *>(smem + kOffBar + 8 * (4 * kStages + 1) + 8);   // [8] per-warp max ||c_k||^2
-    static_assert(8 * (4 * kStages + 1) + 8 + 32 <= 256, "barrier region");
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(smem + kOffBar + 8 * (4 * kStages + 2));
+    float *s_cn2 = reinterpret_cast<float *>(smem + kOffBar + 8 * (4 * kStages + 2) + 8);   // [8] per-warp max ||c_k||^2
+    static_assert(8 * (4 * kStages + 2) + 8 + 32 <= 256, "barrier region");
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -257,12 +258,24 @@ hsq_search_tc_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    // rescoring planes (see exact_score): 4 planes x 256 codewords x 2 halves x 4 units
+    // rescoring planes (see exact_score): 4 planes x 256 codewords x 2 halves x 4 units, exact fp32;
+    // and the MMA's B operand: the codebook rounded to nearest TF32 (see kMargin), written in the
+    // K-major SWIZZLE_64B layout the descriptor expects (row k = 64 bytes, 16-byte unit u at
+    // u ^ ((k >> 1) & 3)) -- by these threads, not by TMA, since it has to be rounded anyway
     for (int i = threadIdx.x; i < kPlanes * kK * 8; i += kThreads) {
         const int u = i & 3, h = (i >> 2) & 1, k = (i >> 3) & (kK - 1), r = i >> 11;
         const float4 val = __ldg(reinterpret_cast<const float4 *>(codebook) + k * 4 + u);
         *reinterpret_cast<float4 *>(s_planes + r * kPlaneBytes + k * 128 + 16 * (4 * h + ((u + r) & 3))) = val;
+        if (r == 0 && h == 0) {
+            uint4 t;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t.x) : "f"(val.x));
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t.y) : "f"(val.y));
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t.z) : "f"(val.z));
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t.w) : "f"(val.w));
+            *reinterpret_cast<uint4 *>(s_cb + k * 64 + ((u ^ ((k >> 1) & 3)) << 4)) = t;
+        }
     }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // operand writes -> visible to the tensor core
     // largest codeword norm: the error bound (hence the margin) scales with it, so the search stays
     // exact for a codebook that is not unit-norm; a non-finite codebook disables the filter
     if (threadIdx.x < kK) {
@@ -297,8 +310,6 @@ hsq_search_tc_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_
     if (warp == 0) {
         // ------------------------------------------------------ TMA producer ---
         if (lane == 0) {
-            mbar_expect_tx(bar_cb, kCbBytes);
-            tma_load_2d(smem_u32(s_cb), &map_cb, bar_cb, 0, 0);
             for (int it = 0; it < my_tiles; ++it) {
                 const int s = it % kStages;
                 const int64_t tile = tile0 + it;
@@ -311,7 +322,6 @@ hsq_search_tc_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_
     } else if (warp == 1) {
         // -------------------------------------------------------- MMA issuer ---
         if (lane == 0) {
-            mbar_wait(bar_cb, 0);
             const uint64_t bdesc = make_desc(smem_u32(s_cb));
             for (int it = 0; it < my_tiles; ++it) {
                 const int s = it % kStages;

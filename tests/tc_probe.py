@@ -47,8 +47,10 @@ def run(n_chunks, kind, dbg_tiles=0):
         exact = O.hsq_scores(x.reshape(-1, 16)[:rows], cb)
         nv = np.linalg.norm(x.reshape(-1, 16)[:rows].astype(np.float64), axis=1)
         err = np.abs(approx.astype(np.float64) - exact.astype(np.float64)).max(1) / np.maximum(nv, 1e-300)
+        eps = 1.5 / 1024 + 4e-6   # hsq_tc.cu kMargin / 2 (unit-norm codebook)
         print("   TF32 score error / ||v||: max %.3e  mean %.3e   (eps used: %.3e, margin 2eps %.3e)"
-              % (err.max(), err.mean(), 1.5 / 512, 3.0 / 512), flush=True)
+              % (err.max(), err.mean(), eps, 2 * eps), flush=True)
+        assert err.max() < eps, "approximation error exceeds the bound the rescoring margin is built on"
         print("   approx-argmax == exact-argmax on %.4f of rows"
               % (np.abs(approx).argmax(1) == np.abs(exact).argmax(1)).mean(), flush=True)
     return bad + badu
