@@ -650,15 +650,32 @@ hsq_decode_reduce_staged_kernel(const uint8_t *__restrict__ codes, const uint8_t
             if (c0 + sl * 32 >= n_chunks) break;
             const bool ok = c < n_chunks;
             const int seg = ok ? cached_segment(segc, seg_start, n_seg, c) : 0;
+            // Three or more users: when the whole slot lies in one tensor (almost always), a lane
+            // hands (code, level) of TWO users to the writers in one shuffle and the writers
+            // dequantize the norm themselves (same three rounded operations) -- the kernel is bound
+            // by the LSU/shuffle pipe there, not by ALU.  Otherwise: code and norm, one shuffle each.
+            constexpr bool kPack = NU >= 3;
+            const int seg0 = __shfl_sync(0xffffffffu, seg, 0);
+            const bool uni = kPack && __all_sync(0xffffffffu, !ok || seg == seg0);
             uint32_t code[NU];
-            float nrm[NU];
+            float nrm[NU];          // !uni: dequantized norm of this lane's chunk; uni: lb of (user, tensor)
+            float den[NU];          // uni: ub - lb of (user, tensor)
+            uint32_t pk[(NU + 1) / 2];
 #pragma unroll
             for (int u = 0; u < NU; ++u) {
-                code[u] = lds_u8(st + (uint32_t)((u * 2) * kStTile + sl * 32 + lane)) << 7;   // byte offset of the slot
-                const float lv = (float)(int)lds_u8(st + (uint32_t)((u * 2 + 1) * kStTile + sl * 32 + lane));
-                const float2 b = s_lbub[u * n_seg + seg];
-                // l * (ub - lb) / 2^n + lb   (probabilistic_scalar_compressor.py:31-32)
-                nrm[u] = __fadd_rn(__fmul_rn(__fmul_rn(lv, __fsub_rn(b.y, b.x)), inv_s), b.x);
+                const uint32_t cb8 = lds_u8(st + (uint32_t)((u * 2) * kStTile + sl * 32 + lane));
+                const uint32_t lv8 = lds_u8(st + (uint32_t)((u * 2 + 1) * kStTile + sl * 32 + lane));
+                const float2 b = s_lbub[u * n_seg + (uni ? seg0 : seg)];
+                code[u] = cb8 << 7;   // byte offset of the codeword's slot
+                den[u] = __fsub_rn(b.y, b.x);
+                if (uni) {
+                    nrm[u] = b.x;
+                    const uint32_t h = cb8 | (lv8 << 8);
+                    if (u & 1) pk[u >> 1] |= h << 16; else pk[u >> 1] = h;
+                } else {
+                    // l * (ub - lb) / 2^n + lb   (probabilistic_scalar_compressor.py:31-32)
+                    nrm[u] = __fadd_rn(__fmul_rn(__fmul_rn((float)(int)lv8, den[u]), inv_s), b.x);
+                }
             }
             const int64_t f0 = (c0 + sl * 32) * 4;
 #pragma unroll
@@ -666,11 +683,24 @@ hsq_decode_reduce_staged_kernel(const uint8_t *__restrict__ codes, const uint8_t
                 const int owner = r * 8 + (lane >> 2);
                 float4 cw[NU];
                 float nm[NU];
+                if (uni) {
 #pragma unroll
-                for (int u = 0; u < NU; ++u) {
-                    const uint32_t cd = __shfl_sync(0xffffffffu, code[u], owner);
-                    nm[u] = __shfl_sync(0xffffffffu, nrm[u], owner);
-                    cw[u] = lds128(cb_lane + cd);
+                    for (int j = 0; j < (NU + 1) / 2; ++j) {
+                        const uint32_t w = __shfl_sync(0xffffffffu, pk[j], owner);
+                        cw[2 * j] = lds128(cb_lane + ((w & 0xffu) << 7));
+                        nm[2 * j] = __fadd_rn(__fmul_rn(__fmul_rn((float)(int)((w >> 8) & 0xffu), den[2 * j]), inv_s), nrm[2 * j]);
+                        if (2 * j + 1 < NU) {
+                            cw[2 * j + 1] = lds128(cb_lane + (((w >> 16) & 0xffu) << 7));
+                            nm[2 * j + 1] = __fadd_rn(__fmul_rn(__fmul_rn((float)(int)(w >> 24), den[2 * j + 1]), inv_s), nrm[2 * j + 1]);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < NU; ++u) {
+                        const uint32_t cd = __shfl_sync(0xffffffffu, code[u], owner);
+                        nm[u] = __shfl_sync(0xffffffffu, nrm[u], owner);
+                        cw[u] = lds128(cb_lane + cd);
+                    }
                 }
                 float2 a0 = mul2(make_float2(cw[0].x, cw[0].y), nm[0]);
                 float2 a1 = mul2(make_float2(cw[0].z, cw[0].w), nm[0]);
