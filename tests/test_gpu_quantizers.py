@@ -101,3 +101,34 @@ def test_sgd_identity_quantizer():
     q.apply()
     for i, p in enumerate(params):
         assert np.array_equal(p.grad.data.cpu().numpy(), (xs[0][i] + xs[1][i]) / np.float32(2))
+
+
+@pytest.mark.parametrize("c_dim,n_bit,users", [(16, 6, 3), (16, 32, 2), (8, 6, 3), (32, 6, 2), (16, 6, 9)])
+def test_identity_tensors_follow_every_hsq_path(c_dim, n_bit, users):
+    """The small (identity) tensors ride inside the HSQ init / staged decode kernels when those
+    run (d = 16, 6-bit norms, <= 8 users) and are launched on their own otherwise (fp32 norms:
+    no init kernel; d = 8 / 32: other decode kernels; 9 users: no attachment): same results."""
+    from util import codebook
+    shapes = [(96, 128), (10,), (64, 64), (999,)]
+    sizes = [int(np.prod(s)) for s in shapes]
+    a = make_args(num_users=users, c_dim=c_dim, n_bit=n_bit, random=False)
+    params = [torch.nn.Parameter(torch.zeros(s, device=DEV)) for s in shapes]
+    q = gq_b200.Quantizer(gq_b200.NearestNeighborCompressor, params, a)
+    assert q.plan is not None
+    xs = [[gen_input(300 + 10 * u + i, n).reshape(s) for i, (n, s) in enumerate(zip(sizes, shapes))]
+          for u in range(users)]
+    for u in range(users):
+        for p, x in zip(params, xs[u]):
+            p.grad = torch.from_numpy(x).to(DEV)
+        q.record(u, epoch=0)
+    q.apply()
+    codecs = [O.HSQ(n, s, codebook(O.chunk_dim(n, c_dim), 256), n_bit, False) if n > 1000 else O.Identity()
+              for n, s in zip(sizes, shapes)]
+    ref = O.ps_step(codecs, xs, O.UniformStream(np.zeros(0, np.float32)))
+    for p, r_ in zip(params, ref):
+        got = p.grad.data.cpu().numpy()
+        r_ = r_.reshape(got.shape)
+        if got.size >= 256:
+            assert np.array_equal(got, r_)
+        else:
+            assert np.abs(got - r_).max() <= 1e-6 * max(np.abs(r_).max(), 1e-30)
