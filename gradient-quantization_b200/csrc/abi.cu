@@ -183,6 +183,19 @@ int gq_hsq_encode(const float *grad, int64_t n_chunks, int d, const float *codeb
         return hsq_encode_tc_fused(grad, n_chunks, codebook, codes, u_out, seg_start, n_seg, keys, barrier, n_bit,
                                    random, uniforms, philox_seed, philox_offset, (uint8_t *)l, lbub, st);
     }
+    static const bool in_kernel_init = [] { const char *f = getenv("GQ_TC_INIT"); return !(f && atoi(f) == 0); }();
+    if (n_bit != 32 && in_kernel_init && algo != GQ_ALGO_EXACT && n_chunks > 0 && hsq_tc_supported(d, K, code_bytes)) {
+        // tcgen05 path: the search kernel resets the keys and carries the rider itself
+        e = validate_group(grad, n_chunks, d, codebook, K, seg_start, n_seg);
+        if (e) return e;
+        GQ_REQUIRE(codes && u_out, "null output pointer");
+        GQ_REQUIRE(((uintptr_t)grad & 15) == 0, "gradient must be 16-byte aligned");
+        e = hsq_search_tc_prepared(grad, n_chunks, codebook, codes, u_out, seg_start, n_seg, keys,
+                                   reinterpret_cast<uint64_t *>(barrier) + 1, rider, st);
+        if (e) return e;
+        return gq_norm_quantize(u_out, n_chunks, seg_start, n_seg, n_bit, random, uniforms, philox_seed,
+                                philox_offset, l, l_bytes, lbub, keys, /*precomputed=*/1, stream);
+    }
     if (n_bit != 32) {
         e = launch_minmax_init_rider(keys, n_seg, st, nullptr, rider);
         if (e) return e;

@@ -50,6 +50,12 @@ int hsq_search_tc(const float *grad, int64_t n_chunks, int d, const float *codeb
                   void *codes, int code_bytes, float *u_out, const int64_t *seg_start, int n_seg,
                   uint32_t *minmax_keys, void *workspace, size_t workspace_bytes, cudaStream_t st);
 
+// same, and the kernel itself resets the min/max keys (flag: 8-byte scratch word in the workspace)
+// and runs `rider`: an encode without a separate init launch
+int hsq_search_tc_prepared(const float *grad, int64_t n_chunks, const float *codebook, void *codes, float *u_out,
+                           const int64_t *seg_start, int n_seg, uint32_t *minmax_keys, uint64_t *flag,
+                           const Rider &rider, cudaStream_t st);
+
 // hsq_tc.cu: search + grid barrier + n-bit norm quantization in ONE persistent kernel
 // (keys must have been initialised and *barrier zeroed by launch_minmax_init before)
 int hsq_encode_tc_fused(const float *grad, int64_t n_chunks, const float *codebook, void *codes, float *u_out,

@@ -20,7 +20,9 @@
 // or vanishing norm rescore all 256 codewords (all-zero rows: codeword 0).
 #include <cuda.h>
 #include <stdlib.h>
+#include <time.h>
 
+#include <atomic>
 #include <mutex>
 #include <vector>
 
@@ -205,13 +207,24 @@ struct TcTail {
     int random;
 };
 
+// Optional in-kernel preparation, so that an encode needs no separate init launch: CTA 0 resets the
+// per-tensor min/max keys and then publishes `id` (unique per launch) in *flag; every epilogue warp
+// checks the flag once, before its first min/max update (about a tile's worth of work later, so
+// it practically never waits).  The spare warps 2-3 of every CTA also run the attached small
+// reduction (the identity tensors' copy into the record).  flag == nullptr: keys are ready.
+struct TcInit {
+    unsigned long long *flag;
+    unsigned long long id;
+    Rider rider;
+};
+
 template <int kEpiGroups, bool kDebug>
 __global__ void __launch_bounds__(128 + 128 * kEpiGroups, 1)
 hsq_search_tc_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_constant__ CUtensorMap map_cb,
                      const float *__restrict__ codebook, int64_t n_chunks, uint8_t *__restrict__ codes,
                      float *__restrict__ u_out,
                      const int64_t *__restrict__ seg_start, int n_seg, uint32_t *__restrict__ minmax_keys,
-                     float *__restrict__ dbg_scores, int dbg_tiles, int flags, const TcTail tail)
+                     float *__restrict__ dbg_scores, int dbg_tiles, int flags, const TcTail tail, const TcInit init)
 {
     constexpr int kThreads = 128 + 128 * kEpiGroups;
     pdl_launch_dependents();
@@ -338,8 +351,19 @@ hsq_search_tc_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_
                 GQ_TRACE(1, it);
             }
         }
+    } else if (warp < 4) {
+        // ------------------------------------- spare warps 2, 3: preparation ---
+        if (init.flag != nullptr && blockIdx.x == 0 && warp == 3) {
+            for (int i = lane; i < 2 * n_seg; i += 32) minmax_keys[i] = (i & 1) ? GQ_KEY_MAX_INIT : GQ_KEY_MIN_INIT;
+            __threadfence();
+            __syncwarp();
+            if (lane == 0)
+                asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(init.flag), "l"(init.id) : "memory");
+        }
+        rider_run(init.rider, (int64_t)blockIdx.x * 64 + (threadIdx.x - 64), (int64_t)gridDim.x * 64);
     } else if (warp >= 4) {
         // ----------------------------------------------------------- epilogue ---
+        bool keys_ready = init.flag == nullptr;
         const int egroup = (warp - 4) >> 2;   // handles local tiles it = egroup (mod kEpiGroups)
         const int quad = warp & 3;            // TMEM lane quadrant this warp may read
         const int row = quad * 32 + lane;     // row of the tile == TMEM lane
@@ -517,6 +541,17 @@ hsq_search_tc_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_
                 u_out[c] = best_u;
             }
             if (minmax_keys != nullptr) {
+                if (!keys_ready) {   // CTA 0 has reset the keys (see TcInit); bounded wait, then trap
+                    unsigned long long seen;
+                    uint32_t spins = 0;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(init.flag) : "memory");
+                        if (seen == init.id) break;
+                        __nanosleep(64);
+                    } while (++spins < (1u << 22));
+                    if (seen != init.id) __trap();
+                    keys_ready = true;
+                }
                 const int seg = valid ? cached_segment(segc, seg_start, n_seg, c) : -1;
                 minmax_add_warp(mm, valid, seg, best_u, minmax_keys);
             }
@@ -619,7 +654,7 @@ size_t hsq_tc_workspace_bytes(int64_t) { return 0; }
 
 static int launch_tc(const float *grad, int64_t n_chunks, const float *codebook, void *codes, float *u_out,
                      const int64_t *seg_start, int n_seg, uint32_t *minmax_keys, float *dbg_scores,
-                     int dbg_tiles, const tc::TcTail &tail, cudaStream_t st)
+                     int dbg_tiles, const tc::TcTail &tail, cudaStream_t st, const tc::TcInit &init = tc::TcInit{})
 {
     GQ_REQUIRE(((uintptr_t)grad & 15) == 0 && ((uintptr_t)codebook & 15) == 0, "TMA needs 16-byte aligned bases");
     GQ_REQUIRE(n_chunks < ((int64_t)1 << 31) - 256, "n_chunks too large for one tensor map");
@@ -646,7 +681,7 @@ static int launch_tc(const float *grad, int64_t n_chunks, const float *codebook,
         GQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes)); \
         GQ_CUDA(launch_pdl(kern, dim3(grid), dim3(128 + 128 * G), (size_t)tc::kSmemBytes, st, mg, mc, codebook,     \
                            n_chunks, (uint8_t *)codes, u_out, seg_start, n_seg, minmax_keys, dbg_scores,        \
-                           dbg_tiles, flags, tail));                                                           \
+                           dbg_tiles, flags, tail, init));                                                     \
     } while (0)
     if (dbg) {
         if (groups == 3) GQ_TC_LAUNCH(3, true); else GQ_TC_LAUNCH(2, true);
@@ -682,6 +717,26 @@ int hsq_encode_tc_fused(const float *grad, int64_t n_chunks, const float *codebo
     tail.s = (float)(1u << n_bit);
     tail.random = random;
     return launch_tc(grad, n_chunks, codebook, codes, u_out, seg_start, n_seg, minmax_keys, nullptr, 0, tail, st);
+}
+
+// search that also resets the min/max keys (no separate init launch) and carries `rider`
+int hsq_search_tc_prepared(const float *grad, int64_t n_chunks, const float *codebook, void *codes, float *u_out,
+                           const int64_t *seg_start, int n_seg, uint32_t *minmax_keys, uint64_t *flag,
+                           const Rider &rider, cudaStream_t st)
+{
+    // launch ids never repeat within a process; the random upper half makes a stale or
+    // uninitialised flag word equal to a live id with probability 2^-64
+    static std::atomic<unsigned long long> counter{[] {
+        unsigned long long seed = (unsigned long long)(uintptr_t)&seed ^ (unsigned long long)clock();
+        seed = seed * 6364136223846793005ull + 1442695040888963407ull;
+        return (seed >> 16) << 32;
+    }()};
+    tc::TcInit init;
+    init.flag = reinterpret_cast<unsigned long long *>(flag);
+    init.id = counter.fetch_add(1) + 1;
+    init.rider = rider;
+    tc::TcTail tail = {};
+    return launch_tc(grad, n_chunks, codebook, codes, u_out, seg_start, n_seg, minmax_keys, nullptr, 0, tail, st, init);
 }
 
 int hsq_search_tc(const float *grad, int64_t n_chunks, int d, const float *codebook, int K, void *codes,

@@ -403,9 +403,17 @@ class FusedPlan:
 
     def launches_per_encode(self):
         per = {"hsq": 3, "qsgd": 3, "sign": 1, "topk": 12, "identity": 1}
-        n = sum(per[g.kind] - (1 if (g.kind == "hsq" and g.n_bit == 32) else 0) for g in self.groups)
+        n = 0
+        for g in self.groups:
+            k = per[g.kind]
+            if g.kind == "hsq" and g.n_bit == 32:
+                k -= 2          # search only
+            elif (g.kind == "hsq" and g.dim == 16 and g.K == 256 and g.code_bytes == 1
+                  and self.algo != _lib.ALGO_EXACT):
+                k -= 1          # tcgen05 search resets the min/max keys itself: search + quantize
+            n += k
         ident, carrier = self._rider_pair()
-        if carrier is not None and carrier.n_bit != 32:   # the copy rides in the HSQ init kernel
+        if carrier is not None and carrier.n_bit != 32:   # the copy rides in the HSQ init / search kernel
             n -= 1
         return n
 
