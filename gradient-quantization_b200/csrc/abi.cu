@@ -159,7 +159,7 @@ int gq_hsq_encode(const float *grad, int64_t n_chunks, int d, const float *codeb
     }
     GQ_REQUIRE(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
     cudaStream_t st = as_stream(stream);
-    const Rider rider = take_rider();   // attached identity copy, if any: rides in the init kernel
+    const Rider rider = take_rider();   // attached identity copy, if any: rides in the search (tcgen05) or init kernel
     uint32_t *keys = reinterpret_cast<uint32_t *>(workspace);
     const size_t keys_bytes = align_up((size_t)n_seg * 2 * sizeof(uint32_t), 256);
     uint32_t *barrier = reinterpret_cast<uint32_t *>((char *)workspace + keys_bytes);

@@ -220,7 +220,7 @@ struct TcInit {
 
 template <int kEpiGroups, bool kDebug>
 __global__ void __launch_bounds__(128 + 128 * kEpiGroups, 1)
-hsq_search_tc_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_constant__ CUtensorMap map_cb,
+hsq_search_tc_kernel(const __grid_constant__ CUtensorMap map_grad,
                      const float *__restrict__ codebook, int64_t n_chunks, uint8_t *__restrict__ codes,
                      float *__restrict__ u_out,
                      const int64_t *__restrict__ seg_start, int n_seg, uint32_t *__restrict__ minmax_keys,
@@ -658,10 +658,8 @@ static int launch_tc(const float *grad, int64_t n_chunks, const float *codebook,
 {
     GQ_REQUIRE(((uintptr_t)grad & 15) == 0 && ((uintptr_t)codebook & 15) == 0, "TMA needs 16-byte aligned bases");
     GQ_REQUIRE(n_chunks < ((int64_t)1 << 31) - 256, "n_chunks too large for one tensor map");
-    CUtensorMap mg, mc;
+    CUtensorMap mg;
     int e = tc::make_map(&mg, grad, n_chunks, tc::kTileM);
-    if (e) return e;
-    e = tc::make_map(&mc, codebook, tc::kK, tc::kK);
     if (e) return e;
     const int64_t n_tiles = (n_chunks + tc::kTileM - 1) / tc::kTileM;
     int sms = sm_count();
@@ -679,7 +677,7 @@ static int launch_tc(const float *grad, int64_t n_chunks, const float *codebook,
     do {                                                                                                       \
         auto kern = tc::hsq_search_tc_kernel<G, DBG>;                                                          \
         GQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes)); \
-        GQ_CUDA(launch_pdl(kern, dim3(grid), dim3(128 + 128 * G), (size_t)tc::kSmemBytes, st, mg, mc, codebook,     \
+        GQ_CUDA(launch_pdl(kern, dim3(grid), dim3(128 + 128 * G), (size_t)tc::kSmemBytes, st, mg, codebook,         \
                            n_chunks, (uint8_t *)codes, u_out, seg_start, n_seg, minmax_keys, dbg_scores,        \
                            dbg_tiles, flags, tail, init));                                                     \
     } while (0)

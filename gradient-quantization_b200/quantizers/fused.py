@@ -281,9 +281,9 @@ class FusedPlan:
     # --------------------------------------------------------------- encode ---
     def encode(self, user, src=None, uniforms=None):
         """Compress the arena (or `src`, laid out like it) into records[user].
-        Launches: HSQ 3 per group (init, search, quantize), QSGD 3, sign 1, top-k 12; the copy of
-        the identity tensors rides in the first HSQ group's init kernel (1 launch of its own
-        when there is no HSQ group)."""
+        Launches: HSQ 2 per group on the tcgen05 path (search, quantize; 3 with the separate init
+        kernel of the exact path), QSGD 3, sign 1, top-k 12; the copy of the identity tensors rides
+        in the first HSQ group's first kernel (1 launch of its own when there is no HSQ group)."""
         src = self.arena if src is None else src
         src_ptr = src if isinstance(src, int) else src.data_ptr()   # tensor or raw device address
         rec = self.records[user]
