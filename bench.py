@@ -458,7 +458,7 @@ def main():
         "gpu_launches": K * (plan.launches_per_encode() + plan.launches_per_decode(world) + exchange_launches),
         "clocks": clocks,
     }
-    if not a.no_cpu_baseline:
+    if not a.no_cpu_baseline and world == 1:   # reported at N = 1 only (torchrun pins OMP to one thread per rank)
         v, dt, elems, threads = cpu_oracle_pass(shapes, 1, None, repeats=3)
         tv, tthreads = cpu_torch_ops_pass()
         line["cpu_baseline"] = {
