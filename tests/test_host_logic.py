@@ -109,3 +109,40 @@ def test_install_dropin_registers_reference_module_names():
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+def test_plan_locates_arena_shaped_gradients_and_counts_launches():
+    a = make_args()
+    plan = FusedPlan(gq_b200.NearestNeighborCompressor, FCN_SHAPES, a, torch.device("cpu"), 2)
+    buf = torch.zeros(plan.arena_elems + 64)
+    off = (-buf.data_ptr() // 4) % 64            # a 256-byte aligned start inside buf
+    flat = buf[off:off + plan.arena_elems]
+    views = plan.views(flat)
+    assert plan.locate(views) == flat.data_ptr()                 # laid out like the arena: read in place
+    moved = list(views)
+    moved[1] = torch.zeros_like(views[1])                        # one tensor lives elsewhere: copy path
+    assert plan.locate(moved) is None
+    assert plan.locate(views[:-1]) is None
+    # ResNet-50 / HSQ d=16 K=256 n=6: search (resets the keys, carries the identity copy) + quantize,
+    # and one decode kernel that also reduces the identity tensors
+    big = FusedPlan(gq_b200.NearestNeighborCompressor, resnet50_shapes(), a, torch.device("cpu"), 2)
+    assert big.launches_per_encode() == 2 and big.launches_per_decode(2) == 1
+    from gq_b200 import _lib
+    exact = FusedPlan(gq_b200.NearestNeighborCompressor, resnet50_shapes(), make_args(hsq_algo=_lib.ALGO_EXACT),
+                      torch.device("cpu"), 2)
+    assert exact.launches_per_encode() == 3                      # init + search + quantize
+    d8 = FusedPlan(gq_b200.NearestNeighborCompressor, resnet50_shapes(), make_args(c_dim=8), torch.device("cpu"), 2)
+    assert d8.launches_per_encode() == 3 and d8.launches_per_decode(2) == 2   # identity reduce on its own
+
+
+def test_peer_records_row_and_address_arithmetic():
+    from gq_b200.quantizers.p2p import PeerRecords
+    pr = object.__new__(PeerRecords)
+    pr.record_bytes, pr.rank, pr.world, pr.step = 4096, 2, 4, 0
+    pr.base = [0x1000000 * (r + 1) for r in range(4)]
+    assert pr.parity == 0 and pr.row() == 2 and pr.row(0) == 0
+    assert pr._addr(1, 3) == pr.base[1] + 3 * 4096               # user 3's row inside rank 1's block
+    offs = list(pr.user_offsets())
+    assert offs[0] == 0 and offs[3] == (pr.base[3] + 3 * 4096) - pr.base[0]
+    pr.step = 1                                                  # odd step: second half of the block
+    assert pr.parity == 1 and pr.row() == 4 + 2 and pr.user0_record_ptr() == pr.base[0] + 4 * 4096
