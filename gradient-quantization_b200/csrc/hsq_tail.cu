@@ -599,11 +599,6 @@ hsq_decode_reduce_staged_kernel(const uint8_t *__restrict__ codes, const uint8_t
         s_cb[i] = __ldg(reinterpret_cast<const float4 *>(codebook) + (i >> 3) * 4 + (i & 3));
     __syncthreads();
     pdl_wait();   // the records are complete (and, across GPUs, announced by the barrier kernel)
-    for (int i = tid; i < NU * n_seg; i += kDecodeThreads) {
-        const int u = i / n_seg, sg = i - u * n_seg;
-        const float2 *b = reinterpret_cast<const float2 *>(reinterpret_cast<const char *>(lbub) + s_off[u]);
-        s_lbub[i] = __ldcv(b + sg);
-    }
     const int64_t n_tiles = (n_chunks + kStTile - 1) / kStTile;
     auto issue = [&](int64_t tile, int buf) {
         const int64_t c0 = tile * kStTile;
@@ -632,7 +627,14 @@ hsq_decode_reduce_staged_kernel(const uint8_t *__restrict__ codes, const uint8_t
     int64_t tile = blockIdx.x;
     int buf = 0;
     if (tile < n_tiles) issue(tile, 0);
-    // the attached small reduction (identity tensors) runs while the first tile is in flight
+    // while the first tile is in flight: the users' (lb, ub) tables (read before the first decode,
+    // i.e. after the block barrier that follows the tile's arrival) ...
+    for (int i = tid; i < NU * n_seg; i += kDecodeThreads) {
+        const int u = i / n_seg, sg = i - u * n_seg;
+        const float2 *b = reinterpret_cast<const float2 *>(reinterpret_cast<const char *>(lbub) + s_off[u]);
+        s_lbub[i] = __ldcv(b + sg);
+    }
+    // ... and the attached small reduction (identity tensors)
     rider_run(rider, (int64_t)blockIdx.x * kDecodeThreads + tid, (int64_t)gridDim.x * kDecodeThreads);
     for (; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
         const int64_t next = tile + gridDim.x;
