@@ -47,6 +47,23 @@ bool pdl_enabled()
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// GQ_TC_V=1: first-generation tcgen05 search (hsq_tc.cu) + separate quantize launch; default 2 (hsq_tc2.cu).
+// Read at every call so that one process can A/B the two.
+int tc_generation()
+{
+    const char *f = getenv("GQ_TC_V");
+    return (f && atoi(f) == 1) ? 1 : 2;
+}
+
+static thread_local Tc2Remote g_remote = {};
+void set_remote(const Tc2Remote &r) { g_remote = r; }
+Tc2Remote take_remote()
+{
+    Tc2Remote r = g_remote;
+    g_remote = Tc2Remote{};
+    return r;
+}
+
 }  // namespace gq
 
 using namespace gq;
@@ -108,8 +125,12 @@ int gq_hsq_search(const float *grad, int64_t n_chunks, int d, const float *codeb
         return GQ_ERR_UNSUPPORTED;
     }
     if (tc_ok && algo != GQ_ALGO_EXACT && n_chunks > 0) {
-        return hsq_search_tc(grad, n_chunks, d, codebook, K, codes, code_bytes, u_out, seg_start, n_seg,
-                             minmax_keys, workspace, workspace_bytes, st);
+        if (tc_generation() == 1)
+            return hsq_search_tc(grad, n_chunks, d, codebook, K, codes, code_bytes, u_out, seg_start, n_seg,
+                                 minmax_keys, workspace, workspace_bytes, st);
+        // keys (when given) were initialised by the caller: no in-kernel reset, no tail
+        return hsq_encode_tc2(grad, n_chunks, codebook, codes, u_out, seg_start, n_seg, minmax_keys, nullptr, nullptr,
+                              Rider{}, nullptr, nullptr, st);
     }
     return hsq_search_exact(grad, n_chunks, d, codebook, K, codes, code_bytes, u_out, seg_start, n_seg,
                             minmax_keys, st);
@@ -151,6 +172,9 @@ int gq_hsq_encode(const float *grad, int64_t n_chunks, int d, const float *codeb
                   int l_bytes, float *lbub, float *u_out, void *workspace, size_t workspace_bytes,
                   int algo, gq_stream_t stream)
 {
+    // pending attachments are consumed (hence cleared) first, whatever happens below
+    const Rider rider = take_rider();   // identity copy, if any: rides in the search (tcgen05) or init kernel
+    const Tc2Remote remote = take_remote();
     GQ_REQUIRE(n_bit == 32 || (n_bit >= 1 && n_bit <= 24), "n_bit %d out of range (1..24 or 32)", n_bit);
     const size_t need = gq_hsq_encode_workspace_bytes(n_chunks, d, K, n_seg);
     if (workspace_bytes < need || workspace == nullptr) {
@@ -159,7 +183,6 @@ int gq_hsq_encode(const float *grad, int64_t n_chunks, int d, const float *codeb
     }
     GQ_REQUIRE(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
     cudaStream_t st = as_stream(stream);
-    const Rider rider = take_rider();   // attached identity copy, if any: rides in the search (tcgen05) or init kernel
     uint32_t *keys = reinterpret_cast<uint32_t *>(workspace);
     const size_t keys_bytes = align_up((size_t)n_seg * 2 * sizeof(uint32_t), 256);
     uint32_t *barrier = reinterpret_cast<uint32_t *>((char *)workspace + keys_bytes);
@@ -182,6 +205,32 @@ int gq_hsq_encode(const float *grad, int64_t n_chunks, int d, const float *codeb
         if (e) return e;
         return hsq_encode_tc_fused(grad, n_chunks, codebook, codes, u_out, seg_start, n_seg, keys, barrier, n_bit,
                                    random, uniforms, philox_seed, philox_offset, (uint8_t *)l, lbub, st);
+    }
+    const bool tc2_ok = tc_generation() == 2 && algo != GQ_ALGO_EXACT && n_chunks > 0 && hsq_tc_supported(d, K, code_bytes);
+    if (remote.n > 0 && !(tc2_ok && n_bit != 32 && hsq_tc2_tail_supported(n_seg, n_bit, l_bytes, u_out, uniforms, l, codes))) {
+        set_error("a remote delivery is attached, but this encode cannot run as the fused tcgen05 kernel");
+        return GQ_ERR_UNSUPPORTED;
+    }
+    if (tc2_ok) {
+        e = validate_group(grad, n_chunks, d, codebook, K, seg_start, n_seg);
+        if (e) return e;
+        GQ_REQUIRE(codes && u_out, "null output pointer");
+        uint64_t *flag = reinterpret_cast<uint64_t *>(barrier) + 1;   // barrier word(s) at +0/+4, flag at +8
+        if (n_bit == 32) {   // fp32 norms: search only, the rider still travels with it
+            return hsq_encode_tc2(grad, n_chunks, codebook, codes, u_out, seg_start, n_seg, nullptr, nullptr, nullptr,
+                                  rider, nullptr, nullptr, st);
+        }
+        GQ_REQUIRE(l && lbub, "null output pointer");
+        if (hsq_tc2_tail_supported(n_seg, n_bit, l_bytes, u_out, uniforms, l, codes)) {
+            Tc2Tail tail = {(uint8_t *)l, lbub, uniforms, philox_seed, philox_offset, n_bit, random};
+            return hsq_encode_tc2(grad, n_chunks, codebook, codes, u_out, seg_start, n_seg, keys, flag, barrier, rider,
+                                  &tail, remote.n > 0 ? &remote : nullptr, st);
+        }
+        e = hsq_encode_tc2(grad, n_chunks, codebook, codes, u_out, seg_start, n_seg, keys, flag, nullptr, rider,
+                           nullptr, nullptr, st);
+        if (e) return e;
+        return gq_norm_quantize(u_out, n_chunks, seg_start, n_seg, n_bit, random, uniforms, philox_seed,
+                                philox_offset, l, l_bytes, lbub, keys, /*precomputed=*/1, stream);
     }
     static const bool in_kernel_init = [] { const char *f = getenv("GQ_TC_INIT"); return !(f && atoi(f) == 0); }();
     if (n_bit != 32 && in_kernel_init && algo != GQ_ALGO_EXACT && n_chunks > 0 && hsq_tc_supported(d, K, code_bytes)) {
@@ -218,6 +267,7 @@ int gq_hsq_decode_reduce(const void *codes, int code_bytes, const void *l, int l
                          const int64_t *seg_start, int n_seg, int n_bit, int mean, int accumulate,
                          float *out, gq_stream_t stream)
 {
+    const Rider pending = take_rider();   // consumed first: an early error return must not leave it armed
     int e = validate_group(out, n_chunks, d, codebook, K, seg_start, n_seg);
     if (e) return e;
     GQ_REQUIRE(n_users >= 1, "n_users %d < 1", n_users);
@@ -232,11 +282,13 @@ int gq_hsq_decode_reduce(const void *codes, int code_bytes, const void *l, int l
     }
     GQ_REQUIRE(n_users == 1 || (user_stride_bytes % 4) == 0, "user stride must be a multiple of 4 bytes");
     GQ_REQUIRE(((uintptr_t)out & 15) == 0, "output must be 16-byte aligned");
+    set_rider(pending);
     e = hsq_decode_reduce(codes, code_bytes, l, l_bytes, lbub, norms_f32, user_stride_bytes, nullptr, n_users,
                           n_chunks, d, codebook, K, seg_start, n_seg, n_bit, mean, accumulate, out,
                           as_stream(stream));
+    const Rider left = take_rider();
     if (e) return e;
-    return launch_rider(take_rider(), as_stream(stream));   // no-op when the decode kernel carried it
+    return launch_rider(left, as_stream(stream));   // no-op when the decode kernel carried it
 }
 
 int gq_hsq_decode_reduce_scattered(const void *codes, int code_bytes, const void *l, int l_bytes,
@@ -245,6 +297,7 @@ int gq_hsq_decode_reduce_scattered(const void *codes, int code_bytes, const void
                                    const int64_t *seg_start, int n_seg, int n_bit, int mean, int accumulate,
                                    float *out, gq_stream_t stream)
 {
+    const Rider pending = take_rider();   // consumed first: an early error return must not leave it armed
     int e = validate_group(out, n_chunks, d, codebook, K, seg_start, n_seg);
     if (e) return e;
     GQ_REQUIRE(n_users >= 1 && n_users <= 8 && user_byte_offsets, "1..8 users with an offset table");
@@ -252,10 +305,12 @@ int gq_hsq_decode_reduce_scattered(const void *codes, int code_bytes, const void
     GQ_REQUIRE(n_bit >= 1 && n_bit <= 24 && l && lbub, "quantized norms required (n_bit 1..24)");
     GQ_REQUIRE(l_bytes == 1 || l_bytes == 4, "l_bytes must be 1 or 4");
     GQ_REQUIRE(((uintptr_t)out & 15) == 0, "output must be 16-byte aligned");
+    set_rider(pending);
     e = hsq_decode_reduce(codes, code_bytes, l, l_bytes, lbub, nullptr, 0, user_byte_offsets, n_users, n_chunks,
                           d, codebook, K, seg_start, n_seg, n_bit, mean, accumulate, out, as_stream(stream));
+    const Rider left = take_rider();
     if (e) return e;
-    return launch_rider(take_rider(), as_stream(stream));   // no-op when the decode kernel carried it
+    return launch_rider(left, as_stream(stream));   // no-op when the decode kernel carried it
 }
 
 int gq_f32_reduce_users(const float *in, int64_t user_stride_bytes, int n_users, int64_t n, int mean,

@@ -63,6 +63,38 @@ int hsq_encode_tc_fused(const float *grad, int64_t n_chunks, const float *codebo
                         int n_bit, int random, const float *uniforms, uint64_t seed, uint64_t offset,
                         uint8_t *l, float *lbub, cudaStream_t st);
 
+int tc_generation();   // abi.cu: 1 = hsq_tc.cu + separate quantize launch, 2 (default) = hsq_tc2.cu
+
+// hsq_tc2.cu: second-generation tcgen05 encode (d == 16, K == 256, uint8 codes).  One launch does the
+// key reset, the identity rider, the search and -- when `tail` is given -- the norm quantization
+// behind a grid barrier; with `remote` it also stores every finished record section into the
+// peers' receive blocks (or once through an NVLS multicast mapping) and announces the step epoch.
+struct Tc2Tail {
+    uint8_t *l;
+    float *lbub;
+    const float *uniforms;
+    uint64_t seed, offset;
+    int n_bit, random;
+};
+struct Tc2Remote {
+    int n;                  // remote destinations (0 = none); with multicast: 1
+    int multicast;
+    int64_t delta[7];       // remote address = local record address + delta[i]
+    const uint8_t *ident;   // identity section inside the local record (mirrored too), may be null
+    int64_t ident_bytes;
+    uint32_t *flag[8];      // words that receive `epoch` (st.release.sys) when the record is delivered
+    int n_flag;
+    uint32_t epoch;
+};
+bool hsq_tc2_tail_supported(int n_seg, int n_bit, int l_bytes, const void *u_out, const void *uniforms, const void *l,
+                            const void *codes);
+int hsq_encode_tc2(const float *grad, int64_t n_chunks, const float *codebook, void *codes, float *u_out,
+                   const int64_t *seg_start, int n_seg, uint32_t *keys, uint64_t *flag, uint32_t *barrier,
+                   const Rider &rider, const Tc2Tail *tail, const Tc2Remote *remote, cudaStream_t st);
+// thread-local pending remote delivery of the calling host thread, consumed by the next gq_hsq_encode
+Tc2Remote take_remote();
+void set_remote(const Tc2Remote &r);
+
 // hsq_tail.cu
 int launch_seg_minmax(const float *u, int64_t n, const int64_t *seg_start, int n_seg, uint32_t *keys,
                       cudaStream_t st);

@@ -1,0 +1,898 @@
+// hsq_tc2.cu -- second-generation tcgen05 HSQ encode for d == 16, K == 256 (uint8 codes):
+// ONE launch = min/max key reset + identity rider + TF32 search with exact fp32 rescoring +
+// (after a grid-wide barrier) the n-bit norm quantization of every CTA's own chunk range, and
+// optionally the delivery of the finished record sections into the peers' receive blocks.
+//
+// Same pipeline as hsq_tc.cu (TMA -> smem ring -> 2 x tcgen05.mma kind::tf32 M128 N256 K8 ->
+// two TMEM buffers -> one epilogue thread per row), same exactness argument (every codeword of
+// every group whose approximate maximum lies within 2*eps of the row maximum is rescored with
+// the ascending-j fmaf chain, first index wins).  What changed is the instruction budget of the
+// epilogue, which is what bounds the kernel (ALU pipe / issue slots, not HBM or the tensor pipe):
+//   PAIR   the B operand holds c_{2i} + c_{2i+1} and c_{2i} - c_{2i+1} instead of the codewords:
+//          max(|s_a|, |s_b|) = (|s_a + s_b| + |s_a - s_b|) / 2, so the first reduction level of
+//          the group maxima is one FADD with |.| operand modifiers on the FMA pipe instead of an
+//          FMNMX on the (half as wide, busier) ALU pipe; everything downstream works on doubled
+//          values.  The error bound scales with (||b_p|| + ||b_m||) / 2 <= sqrt(2) max||c||.
+//   FMASK  the 64-group candidate mask is built on the FMA pipe: b_g = sat((gm_g - thr') * S) is
+//          exactly 0 or 1 (S = 2^(24 - exponent(thr)), thr' = the float below thr), accumulated as
+//          m = 2 m + b_g in four fp32 chains whose mantissas are the mask -- no FADD + funnel shift.
+//   F2     rescoring with packed FFMA2 (fma.rn.f32x2): two codewords per instruction, bit-identical
+//          lanes; the codebook planes are pair-interleaved.
+//   waits  mbarrier.try_wait with a suspend-time hint instead of hot polling loops.
+//   tail   norm quantization fused behind a grid barrier (all CTAs are co-resident: grid <= SMs,
+//          one CTA per SM), every thread's loads issued before any is consumed.
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include <atomic>
+#include <mutex>
+
+#include "gq_internal.cuh"
+#include "tc_ptx.cuh"
+
+namespace gq {
+namespace tc2 {
+
+using namespace tcptx;
+
+constexpr int kD = 16;
+constexpr int kK = 256;
+constexpr int kTileM = 128;
+constexpr uint32_t kTileBytes = kTileM * kD * 4;  // 8192
+constexpr uint32_t kCbBytes = kK * kD * 4;        // 16384
+constexpr int kGroup = 4;
+constexpr int kNumGroups = kK / kGroup;           // 64
+constexpr uint32_t kPlanesBytes = 131072;         // rescoring planes (8-fold replicated codebook)
+constexpr int kTailMaxSeg = 1024;                 // segment tables of the fused tail live in the stage ring
+// 2 * eps / (||v|| * norm scale), see hsq_tc.cu (kMargin) for the derivation; the PAIR variant adds
+// the fp32 rounding of c_a +- c_b (2^-24) and of |p| + |m| (2^-24), covered by the larger slack
+constexpr float kMargin = 2.0f * (1.5f / 1024.0f + 4.0e-6f);
+constexpr float kMarginPair = 2.0f * (1.5f / 1024.0f + 8.0e-6f);
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((kK >> 3) << 17) | ((kTileM >> 4) << 24);
+
+template <int G>
+struct Layout {
+    static constexpr int kStages = (G == 4) ? 8 : 6;   // multiple of 2 (TMEM buffers) and of G
+    static constexpr uint32_t kOffA = 0;
+    static constexpr uint32_t kOffCb = kStages * kTileBytes;
+    static constexpr uint32_t kOffPlanes = kOffCb + kCbBytes;
+    static constexpr uint32_t kOffBar = kOffPlanes + kPlanesBytes;
+    static constexpr uint32_t kSmemBytes = kOffBar + 512 + 1024;   // + alignment slack
+};
+
+// Where else the finished record sections go (multi-GPU ps exchange fused into the encode):
+// every address the tail writes inside the local record is also written at address + delta[i].
+struct Remote {
+    int n;                  // number of remote destinations (0: none)
+    int multicast;          // 1: delta[0] leads into an NVLS multicast mapping (multimem.st)
+    int64_t delta[7];
+    const uint8_t *ident;   // identity section of the local record (written by the rider), mirrored too
+    int64_t ident_bytes;    // multiple of 16
+    uint32_t *done;         // local arrival counter (zeroed together with the grid barrier word)
+    uint32_t *flag[8];      // where to announce `epoch` once every CTA has delivered (n_flag entries)
+    int n_flag;
+    uint32_t epoch;
+};
+
+struct Enc2 {
+    const float *codebook;
+    int n_chunks;
+    uint8_t *codes;
+    float *u_out;
+    const int64_t *seg_start;
+    int n_seg;
+    uint32_t *keys;              // [2 * n_seg] min/max keys, nullptr: no min/max wanted
+    unsigned long long *flag;    // in-kernel key reset handshake (nullptr: keys are ready)
+    unsigned long long id;
+    Rider rider;
+    uint8_t *l;                  // fused tail when != nullptr
+    float *lbub;
+    uint32_t *barrier;
+    const float *uniforms;
+    uint64_t seed, offset;
+    float s;
+    int random;
+    Remote remote;
+};
+
+__device__ __forceinline__ float4 lds_f4(uint32_t a)
+{
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ void lds_2x64(uint32_t a, unsigned long long &lo, unsigned long long &hi)
+{
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "r"(a));
+}
+__device__ __forceinline__ unsigned long long pack2(float a, float b)
+{
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float &a, float &b)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fmul2(unsigned long long a, unsigned long long b)
+{
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c)
+{
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ float fma_sat(float a, float b, float c)
+{
+    float r;
+    asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+
+// store 4 bytes / 16 bytes at a local record address and at every remote copy of it
+__device__ __forceinline__ void remote_st32(const Remote &R, void *local, uint32_t v)
+{
+    if (R.multicast) {
+        asm volatile("multimem.st.weak.global.u32 [%0], %1;" ::"l"((char *)local + R.delta[0]), "r"(v) : "memory");
+    } else {
+#pragma unroll
+        for (int i = 0; i < 7; ++i)
+            if (i < R.n) *reinterpret_cast<uint32_t *>((char *)local + R.delta[i]) = v;
+    }
+}
+__device__ __forceinline__ void remote_st128(const Remote &R, void *local, uint4 v)
+{
+    if (R.multicast) {
+        asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                     ::"l"((char *)local + R.delta[0]), "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)),
+                       "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w)) : "memory");
+    } else {
+#pragma unroll
+        for (int i = 0; i < 7; ++i)
+            if (i < R.n) *reinterpret_cast<uint4 *>((char *)local + R.delta[i]) = v;
+    }
+}
+
+template <int G, bool PAIR, bool FMASK, bool F2>
+__global__ void __launch_bounds__(128 + 128 * G, 1)
+hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_constant__ Enc2 P)
+{
+    using L = Layout<G>;
+    constexpr int kThreads = 128 + 128 * G;
+    constexpr int kStages = L::kStages;
+    pdl_launch_dependents();
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t *s_a = smem + L::kOffA;
+    uint8_t *s_cb = smem + L::kOffCb;
+    uint8_t *s_planes = smem + L::kOffPlanes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L::kOffBar);
+    const uint32_t bar_full = smem_u32(bars);
+    const uint32_t bar_empty = bar_full + 8 * kStages;
+    const uint32_t bar_tfull = bar_empty + 8 * kStages;
+    const uint32_t bar_tempty = bar_tfull + 8 * kStages;
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(smem + L::kOffBar + 8 * (4 * kStages));
+    float *s_cn = reinterpret_cast<float *>(smem + L::kOffBar + 8 * (4 * kStages) + 8);   // [8] per-warp norm maxima
+    int *s_misc = reinterpret_cast<int *>(smem + L::kOffBar + 8 * (4 * kStages) + 8 + 32);
+    static_assert(8 * (4 * kStages) + 8 + 32 + 16 <= 512, "barrier region");
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n_chunks = P.n_chunks;
+    const int n_tiles = (n_chunks + kTileM - 1) / kTileM;
+    const int tq = n_tiles / (int)gridDim.x, trem = n_tiles % (int)gridDim.x;
+    const int tile0 = (int)blockIdx.x * tq + min((int)blockIdx.x, trem);
+    const int my_tiles = tq + (((int)blockIdx.x < trem) ? 1 : 0);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 4);
+            mbar_init(bar_tfull + 8 * s, 1);
+            mbar_init(bar_tempty + 8 * s, 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    const float *codebook = P.codebook;
+    // ---- rescoring planes (exact fp32 codewords, replicated so that lane-divergent LDS.128 never conflict)
+    if constexpr (F2) {
+        // 8 planes (one per lane class c = lane & 7) x 128 codeword pairs x 128 bytes; 16-byte unit t of
+        // pair p = (c_2p[2t], c_2p+1[2t], c_2p[2t+1], c_2p+1[2t+1]) stored at bank group (t + c) & 7
+        for (int i = threadIdx.x; i < 8 * 128 * 8; i += kThreads) {
+            const int t = i & 7, p = (i >> 3) & 127, c = i >> 10;
+            const float2 a = __ldg(reinterpret_cast<const float2 *>(codebook + (2 * p) * kD) + t);
+            const float2 b = __ldg(reinterpret_cast<const float2 *>(codebook + (2 * p + 1) * kD) + t);
+            *reinterpret_cast<float4 *>(s_planes + c * 16384 + p * 128 + 16 * ((t + c) & 7)) =
+                make_float4(a.x, b.x, a.y, b.y);
+        }
+    } else {
+        // 4 planes (rotation r) x 256 codewords x 128 bytes: unit u twice (half h) at bank group 4h + ((u + r) & 3)
+        for (int i = threadIdx.x; i < 4 * kK * 8; i += kThreads) {
+            const int u = i & 3, h = (i >> 2) & 1, k = (i >> 3) & (kK - 1), r = i >> 11;
+            const float4 val = __ldg(reinterpret_cast<const float4 *>(codebook) + k * 4 + u);
+            *reinterpret_cast<float4 *>(s_planes + r * 32768 + k * 128 + 16 * (4 * h + ((u + r) & 3))) = val;
+        }
+    }
+    // ---- MMA B operand, K-major SWIZZLE_64B (row k = 64 bytes, unit u at u ^ ((k >> 1) & 3)), rounded
+    //      to nearest TF32; PAIR: row 2i = c_2i + c_2i+1, row 2i+1 = c_2i - c_2i+1
+    for (int i = threadIdx.x; i < kK * 4; i += kThreads) {
+        const int u = i & 3, k = i >> 2;
+        float4 val;
+        if (PAIR) {
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(codebook) + (k & ~1) * 4 + u);
+            const float4 b = __ldg(reinterpret_cast<const float4 *>(codebook) + (k | 1) * 4 + u);
+            val = (k & 1) ? make_float4(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y), __fsub_rn(a.z, b.z), __fsub_rn(a.w, b.w))
+                          : make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z), __fadd_rn(a.w, b.w));
+        } else {
+            val = __ldg(reinterpret_cast<const float4 *>(codebook) + k * 4 + u);
+        }
+        uint4 t;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t.x) : "f"(val.x));
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t.y) : "f"(val.y));
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t.z) : "f"(val.z));
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t.w) : "f"(val.w));
+        *reinterpret_cast<uint4 *>(s_cb + k * 64 + ((u ^ ((k >> 1) & 3)) << 4)) = t;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    // ---- norm scale of the error bound: max ||c_k||, or (PAIR) max over pairs of ||c_a + c_b|| + ||c_a - c_b||
+    if (threadIdx.x < kK) {
+        float val;
+        if (PAIR) {
+            const int p = threadIdx.x >> 1;   // both threads of a pair compute the same value
+            float sp = 0.0f, sm = 0.0f;
+#pragma unroll
+            for (int j = 0; j < kD; ++j) {
+                const float a = __ldg(codebook + (2 * p) * kD + j), b = __ldg(codebook + (2 * p + 1) * kD + j);
+                const float ps = __fadd_rn(a, b), ms = __fsub_rn(a, b);
+                sp = fmaf(ps, ps, sp);
+                sm = fmaf(ms, ms, sm);
+            }
+            val = __fadd_rn(sqrtf(sp), sqrtf(sm));
+        } else {
+            float c2 = 0.0f;
+#pragma unroll
+            for (int j = 0; j < kD; ++j) {
+                const float a = __ldg(codebook + threadIdx.x * kD + j);
+                c2 = fmaf(a, a, c2);
+            }
+            val = sqrtf(c2);
+        }
+        if (!(val < 3.0e38f)) val = __int_as_float(0x7f800000);   // NaN -> +inf so that the max keeps it
+        val = warp_max(val);
+        if (lane == 0) s_cn[warp] = val;
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+    float cn = s_cn[0];
+#pragma unroll
+    for (int w = 1; w < kK / 32; ++w) cn = fmaxf(cn, s_cn[w]);
+    // (a non-finite codebook gives margin = +inf: threshold -inf / NaN, every group is rescored)
+    const float margin = (PAIR ? kMarginPair : kMargin) * (1.0f + 1.0e-5f) * cn;
+    pdl_wait();
+
+    if (warp == 0) {
+        // ------------------------------------------------------ TMA producer ---
+        if (lane == 0) {
+            for (int it = 0; it < my_tiles; ++it) {
+                const int s = it % kStages;
+                mbar_wait_sleep(bar_empty + 8 * s, ((it / kStages) & 1) ^ 1);
+                mbar_expect_tx(bar_full + 8 * s, kTileBytes);
+                tma_load_2d(smem_u32(s_a + s * kTileBytes), &map_grad, bar_full + 8 * s, 0, (tile0 + it) * kTileM);
+            }
+        }
+    } else if (warp == 1) {
+        // -------------------------------------------------------- MMA issuer ---
+        if (lane == 0) {
+            const uint64_t bdesc = make_desc(smem_u32(s_cb));
+            for (int it = 0; it < my_tiles; ++it) {
+                const int s = it % kStages;
+                const int b = it & 1;
+                if (it >= 2) mbar_wait_sleep(bar_tempty + 8 * ((it - 2) % kStages), ((it - 2) / kStages) & 1);
+                mbar_wait_sleep(bar_full + 8 * s, (it / kStages) & 1);
+                tc_fence_after();
+                const uint64_t adesc = make_desc(smem_u32(s_a + s * kTileBytes));
+                const uint32_t taddr = tmem_base + (uint32_t)(b * kK);
+                mma_tf32(taddr, adesc, bdesc, 0u, kIdesc);
+                mma_tf32(taddr, adesc + 2, bdesc + 2, 1u, kIdesc);
+                mma_commit(bar_tfull + 8 * s);
+            }
+        }
+    } else if (warp < 4) {
+        // ------------------------------------- spare warps 2, 3: preparation ---
+        if (P.flag != nullptr && blockIdx.x == 0 && warp == 3) {
+            for (int i = lane; i < 2 * P.n_seg; i += 32) P.keys[i] = (i & 1) ? GQ_KEY_MAX_INIT : GQ_KEY_MIN_INIT;
+            if (lane == 0 && P.barrier != nullptr) {
+                P.barrier[0] = 0u;
+                if (P.remote.done != nullptr) P.remote.done[0] = 0u;
+            }
+            __threadfence();
+            __syncwarp();
+            if (lane == 0)
+                asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(P.flag), "l"(P.id) : "memory");
+        }
+        rider_run(P.rider, (int64_t)blockIdx.x * 64 + (threadIdx.x - 64), (int64_t)gridDim.x * 64);
+    } else {
+        // ----------------------------------------------------------- epilogue ---
+        bool keys_ready = P.flag == nullptr;
+        const int egroup = (warp - 4) >> 2;
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;
+        uint32_t pbase;
+        uint32_t uo[F2 ? 8 : 4];
+        if constexpr (F2) {
+            const int cls = lane & 7;
+            pbase = smem_u32(s_planes) + cls * 16384;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) uo[t] = 16u * ((t + cls) & 7);
+        } else {
+            const int rot = (lane & 7) >> 1, hlf = lane & 1;
+            pbase = smem_u32(s_planes) + rot * 32768 + 64 * hlf;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) uo[u] = 16u * ((u + rot) & 3);
+        }
+        SegCache segc;
+        MinMaxAcc mm;
+        for (int it = egroup; it < my_tiles; it += G) {
+            const int s = it % kStages;
+            const uint32_t ph = (it / kStages) & 1;
+            const int b = it & 1;
+            const int c = (tile0 + it) * kTileM + row;
+            const bool valid = c < n_chunks;
+            mbar_wait_sleep(bar_full + 8 * s, ph);    // TMA data visible to this thread
+            mbar_wait_sleep(bar_tfull + 8 * s, ph);   // accumulators complete
+            __syncwarp();
+            tc_fence_after();
+
+            // ---- pass over the 256 approximate scores of this row: maximum per group of 4 codewords
+            //      (PAIR: doubled values, |p| + |m| per codeword pair)
+            float gm[kNumGroups];
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * kK);
+            {
+                uint32_t sa[16], sb[16];
+                tmem_ld16(taddr, sa);
+                tmem_ld_wait16(sa);
+#pragma unroll
+                for (int h = 0; h < kK / 32; ++h) {
+                    tmem_ld16(taddr + h * 32 + 16, sb);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        if (PAIR) {
+                            const float x0 = __fadd_rn(fabsf(__uint_as_float(sa[4 * g])), fabsf(__uint_as_float(sa[4 * g + 1])));
+                            const float x1 = __fadd_rn(fabsf(__uint_as_float(sa[4 * g + 2])), fabsf(__uint_as_float(sa[4 * g + 3])));
+                            gm[h * 8 + g] = fmaxf(x0, x1);
+                        } else {
+                            const float m = fmaxf(fabsf(__uint_as_float(sa[4 * g])), fabsf(__uint_as_float(sa[4 * g + 1])));
+                            gm[h * 8 + g] = max3(m, fabsf(__uint_as_float(sa[4 * g + 2])), fabsf(__uint_as_float(sa[4 * g + 3])));
+                        }
+                    }
+                    tmem_ld_wait16(sb);
+                    if (h + 1 < kK / 32) tmem_ld16(taddr + h * 32 + 32, sa);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        if (PAIR) {
+                            const float x0 = __fadd_rn(fabsf(__uint_as_float(sb[4 * g])), fabsf(__uint_as_float(sb[4 * g + 1])));
+                            const float x1 = __fadd_rn(fabsf(__uint_as_float(sb[4 * g + 2])), fabsf(__uint_as_float(sb[4 * g + 3])));
+                            gm[h * 8 + 4 + g] = fmaxf(x0, x1);
+                        } else {
+                            const float m = fmaxf(fabsf(__uint_as_float(sb[4 * g])), fabsf(__uint_as_float(sb[4 * g + 1])));
+                            gm[h * 8 + 4 + g] = max3(m, fabsf(__uint_as_float(sb[4 * g + 2])), fabsf(__uint_as_float(sb[4 * g + 3])));
+                        }
+                    }
+                    if (h + 1 < kK / 32) tmem_ld_wait16(sa);
+                }
+            }
+            // TMEM buffer b may be overwritten by the MMA of local tile it + 2
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * s);
+
+            // ---- this row's chunk, from the (swizzled) smem tile
+            float v[kD];
+            {
+                const uint32_t arow = smem_u32(s_a) + s * kTileBytes + row * 64;
+                const int sw = (row >> 1) & 3;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float4 t = lds_f4(arow + ((u ^ sw) << 4));
+                    v[4 * u] = t.x; v[4 * u + 1] = t.y; v[4 * u + 2] = t.z; v[4 * u + 3] = t.w;
+                }
+            }
+            float n2 = 0.0f;
+#pragma unroll
+            for (int j = 0; j < kD; ++j) n2 = fmaf(v[j], v[j], n2);
+            // release the smem stage only after EVERY lane's loads of v have returned (see hsq_tc.cu)
+            const uint32_t all_loaded = __ballot_sync(0xffffffffu, !(n2 < 0.0f));   // always all ones
+            if (lane == 0) mbar_arrive(bar_empty + 8 * s + ((all_loaded == 0u) ? 8u : 0u));
+
+            // ---- row maximum (four chains of FMNMX3) and threshold
+            float am[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                am[q] = max3(gm[16 * q], gm[16 * q + 1], gm[16 * q + 2]);
+#pragma unroll
+                for (int g = 3; g < 15; g += 2) am[q] = max3(am[q], gm[16 * q + g], gm[16 * q + g + 1]);
+                am[q] = fmaxf(am[q], gm[16 * q + 15]);
+            }
+            const float amax = fmaxf(fmaxf(am[0], am[1]), fmaxf(am[2], am[3]));
+            const float thr = amax - margin * sqrtf(n2);
+            // ---- candidate groups: gm[g] >= thr
+            uint32_t clo, chi;
+            bool special;
+            if (FMASK) {
+                // thr in [1e-30, 3e38): S = 2^(24 - e(thr)) is a normal float, (gm - thr') * S is >= 1 for
+                // every gm > thr' (thr' = the float below thr, i.e. gm >= thr) and <= 0 otherwise, so the
+                // saturating FMA yields exactly 1.0 or 0.0; m = 2 m + b accumulates 16 of them exactly.
+                special = !(n2 < 3.0e38f) || !(amax < 3.0e38f) || (n2 < 1.0e-30f) || !(thr >= 1.0e-30f);
+                const uint32_t tb = __float_as_uint(thr);
+                const float thrm = __uint_as_float(tb - 1u);
+                const float S = __uint_as_float(0x8B000000u - (tb & 0x7F800000u));
+                const float T = -__fmul_rn(thrm, S);
+                float mk[4] = {1.0f, 1.0f, 1.0f, 1.0f};
+#pragma unroll
+                for (int g = 15; g >= 0; --g) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) mk[q] = __fmaf_rn(mk[q], 2.0f, fma_sat(gm[16 * q + g], S, T));
+                }
+                clo = ((__float_as_uint(mk[0]) >> 7) & 0xffffu) | ((__float_as_uint(mk[1]) << 9) & 0xffff0000u);
+                chi = ((__float_as_uint(mk[2]) >> 7) & 0xffffu) | ((__float_as_uint(mk[3]) << 9) & 0xffff0000u);
+            } else {
+                special = !(n2 < 3.0e38f) || !(amax < 3.0e38f) || (n2 < 1.0e-30f);
+                uint32_t bl[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                for (int g = 15; g >= 0; --g) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        bl[q] = __funnelshift_l(__float_as_uint(gm[16 * q + g] - thr), bl[q], 1);
+                }
+                clo = ~((bl[0] & 0xffffu) | (bl[1] << 16));
+                chi = ~((bl[2] & 0xffffu) | (bl[3] << 16));
+            }
+            if (special || (clo | chi) == 0u) {
+                // non-finite or vanishing norm, NaN scores, threshold out of range, empty set: rescore
+                // everything; an all-zero row scores +-0 against every codeword: codeword 0 wins
+                uint32_t any = 0u;
+#pragma unroll
+                for (int j = 0; j < kD; ++j) any |= __float_as_uint(v[j]);
+                const bool zero = (any << 1) == 0u;
+                clo = zero ? 1u : 0xffffffffu;
+                chi = zero ? 0u : 0xffffffffu;
+            }
+
+            // ---- exact rescoring of the candidate groups
+            int best_bits = -1, best_k = 0;
+            float best_u = 0.0f;
+            unsigned long long vv[F2 ? kD : 1];
+            if constexpr (F2) {
+#pragma unroll
+                for (int j = 0; j < kD; ++j) vv[j] = pack2(v[j], v[j]);
+            }
+            uint32_t cur = clo, nxt = chi;
+            int gbase = 0;
+            if (cur == 0u) { cur = nxt; nxt = 0u; gbase = 32; }
+            while (cur != 0u) {
+                const int g = gbase + __ffs((int)cur) - 1;
+                cur &= cur - 1u;
+                float p[kGroup];
+                if constexpr (F2) {
+                    const uint32_t slot = pbase + (uint32_t)g * 256u;   // pair 2g at slot, pair 2g + 1 at slot + 128
+                    unsigned long long a01, a23;
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        unsigned long long c0, c1, e0, e1;
+                        lds_2x64(slot + uo[t], c0, c1);
+                        lds_2x64(slot + 128u + uo[t], e0, e1);
+                        if (t == 0) {
+                            a01 = fmul2(c0, vv[0]);
+                            a23 = fmul2(e0, vv[0]);
+                        } else {
+                            a01 = ffma2(c0, vv[2 * t], a01);
+                            a23 = ffma2(e0, vv[2 * t], a23);
+                        }
+                        a01 = ffma2(c1, vv[2 * t + 1], a01);
+                        a23 = ffma2(e1, vv[2 * t + 1], a23);
+                    }
+                    unpack2(a01, p[0], p[1]);
+                    unpack2(a23, p[2], p[3]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < kGroup; ++i) {
+                        const uint32_t rowa = pbase + (uint32_t)(g * kGroup + i) * 128u;
+                        const float4 c0 = lds_f4(rowa + uo[0]);
+                        const float4 c1 = lds_f4(rowa + uo[1]);
+                        const float4 c2 = lds_f4(rowa + uo[2]);
+                        const float4 c3 = lds_f4(rowa + uo[3]);
+                        float acc = __fmul_rn(c0.x, v[0]);
+                        acc = __fmaf_rn(c0.y, v[1], acc);  acc = __fmaf_rn(c0.z, v[2], acc);  acc = __fmaf_rn(c0.w, v[3], acc);
+                        acc = __fmaf_rn(c1.x, v[4], acc);  acc = __fmaf_rn(c1.y, v[5], acc);  acc = __fmaf_rn(c1.z, v[6], acc);
+                        acc = __fmaf_rn(c1.w, v[7], acc);  acc = __fmaf_rn(c2.x, v[8], acc);  acc = __fmaf_rn(c2.y, v[9], acc);
+                        acc = __fmaf_rn(c2.z, v[10], acc); acc = __fmaf_rn(c2.w, v[11], acc); acc = __fmaf_rn(c3.x, v[12], acc);
+                        acc = __fmaf_rn(c3.y, v[13], acc); acc = __fmaf_rn(c3.z, v[14], acc); acc = __fmaf_rn(c3.w, v[15], acc);
+                        p[i] = acc;
+                    }
+                }
+                const float gmax = fmaxf(fmaxf(fabsf(p[0]), fabsf(p[1])), fmaxf(fabsf(p[2]), fabsf(p[3])));
+                const int gb = __float_as_int(gmax);
+                const float psum = (p[0] + p[1]) + (p[2] + p[3]);   // NaN (or inf - inf) takes the slow path
+                if (gb > best_bits || psum != psum) {
+#pragma unroll
+                    for (int i = 0; i < kGroup; ++i) {
+                        const int ab = __float_as_int(p[i]) & 0x7fffffff;
+                        if (ab > best_bits) { best_bits = ab; best_k = g * kGroup + i; best_u = p[i]; }
+                    }
+                }
+                if (cur == 0u) { cur = nxt; nxt = 0u; gbase = 32; }
+            }
+            __syncwarp();
+            if (valid) {
+                P.codes[c] = (uint8_t)best_k;
+                P.u_out[c] = best_u;
+            }
+            if (P.keys != nullptr) {
+                if (!keys_ready) {   // CTA 0 has reset the keys; bounded wait, then trap
+                    unsigned long long seen;
+                    uint32_t spins = 0;
+                    do {
+                        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(P.flag) : "memory");
+                        if (seen == P.id) break;
+                        __nanosleep(64);
+                    } while (++spins < (1u << 22));
+                    if (seen != P.id) __trap();
+                    keys_ready = true;
+                }
+                const int seg = valid ? cached_segment(segc, P.seg_start, P.n_seg, (int64_t)c) : -1;
+                minmax_add_warp(mm, valid, seg, best_u, P.keys);
+            }
+        }
+        if (P.keys != nullptr) minmax_flush_warp(mm, P.keys);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+    if (P.l == nullptr) return;
+
+    // =============================================== fused tail: n-bit norm quantization ===
+    // grid barrier: every CTA's min/max atomics are performed before anyone reads lb/ub
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(P.barrier, 1u);
+        uint32_t seen, spins = 0;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(P.barrier) : "memory");
+            if (seen >= gridDim.x) break;
+            __nanosleep(32);
+        } while (++spins < (1u << 24));
+        if (seen < gridDim.x) __trap();
+    }
+    const int n_seg = P.n_seg;
+    int *s_seg = reinterpret_cast<int *>(smem + L::kOffA);                                   // [n_seg + 1]
+    float2 *s_lbub = reinterpret_cast<float2 *>(smem + L::kOffA + 4 * ((n_seg + 2) & ~1));   // [n_seg]
+    for (int i = threadIdx.x; i <= n_seg; i += kThreads) s_seg[i] = (int)P.seg_start[i];
+    __syncthreads();
+    const Remote &R = P.remote;
+    for (int i = threadIdx.x; i < n_seg; i += kThreads) {
+        const float lb = key_to_float(__ldcg(P.keys + 2 * i)), ub = key_to_float(__ldcg(P.keys + 2 * i + 1));
+        s_lbub[i] = make_float2(lb, ub);
+        if (blockIdx.x == 0) {   // the reference returns lb/ub (probabilistic_scalar_compressor.py:27)
+            P.lbub[2 * i] = lb;
+            P.lbub[2 * i + 1] = ub;
+            if (R.n > 0) {
+                remote_st32(R, P.lbub + 2 * i, __float_as_uint(lb));
+                remote_st32(R, P.lbub + 2 * i + 1, __float_as_uint(ub));
+            }
+        }
+    }
+    __syncthreads();
+    {
+        const int c_begin = tile0 * kTileM;
+        const int c_end = min((tile0 + my_tiles) * kTileM, n_chunks);
+        const int qb = c_begin >> 2, qe = (c_end + 3) >> 2;
+        const float s = P.s;
+        const int random = P.random;
+        const bool ext = random && P.uniforms != nullptr;
+        const bool philox = random && P.uniforms == nullptr;
+        const bool philox_aligned = (P.offset & 3u) == 0;
+        constexpr int J = 5;   // float4 groups per thread and pass: 512 threads x 5 x 4 = 10240 chunks >= 78 tiles
+        int seg = 0;
+        {   // segment of this CTA's first chunk (binary search in shared memory)
+            int lo = 0, hi = n_seg;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (s_seg[mid] <= c_begin) lo = mid; else hi = mid;
+            }
+            seg = lo;
+        }
+        for (int q0 = qb + (int)threadIdx.x; q0 < qe; q0 += J * kThreads) {
+            float4 xv[J], rv[J];
+            uint32_t cw[J];
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                const int q = q0 + j * kThreads;
+                xv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                rv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                cw[j] = 0u;
+                if (q < qe) {
+                    if (q * 4 + 3 < n_chunks) {
+                        xv[j] = __ldcg(reinterpret_cast<const float4 *>(P.u_out) + q);
+                        if (ext) rv[j] = __ldg(reinterpret_cast<const float4 *>(P.uniforms) + q);
+                        if (R.n > 0) cw[j] = __ldcg(reinterpret_cast<const uint32_t *>(P.codes) + q);
+                    } else {
+                        float x[4] = {0.f, 0.f, 0.f, 0.f}, r[4] = {0.f, 0.f, 0.f, 0.f};
+                        for (int t = 0; t < 4; ++t) {
+                            if (q * 4 + t < n_chunks) {
+                                x[t] = __ldcg(P.u_out + q * 4 + t);
+                                if (ext) r[t] = __ldg(P.uniforms + q * 4 + t);
+                                if (R.n > 0) cw[j] |= (uint32_t)__ldcg(P.codes + q * 4 + t) << (8 * t);
+                            }
+                        }
+                        xv[j] = make_float4(x[0], x[1], x[2], x[3]);
+                        rv[j] = make_float4(r[0], r[1], r[2], r[3]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                const int q = q0 + j * kThreads;
+                if (q >= qe) continue;
+                const int i0 = q * 4;
+                const float x[4] = {xv[j].x, xv[j].y, xv[j].z, xv[j].w};
+                float r[4] = {rv[j].x, rv[j].y, rv[j].z, rv[j].w};
+                if (philox) {
+                    if (philox_aligned) {
+                        const uint4 w = philox4x32_10(P.seed, (P.offset + (uint64_t)i0) >> 2);
+                        r[0] = u01(w.x); r[1] = u01(w.y); r[2] = u01(w.z); r[3] = u01(w.w);
+                    } else {
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) r[t] = philox_uniform(P.seed, P.offset, (uint64_t)(i0 + t));
+                    }
+                }
+                while (i0 >= s_seg[seg + 1]) ++seg;
+                int lv[4];
+                if (i0 + 3 < s_seg[seg + 1]) {   // all four chunks in one tensor
+                    const float2 bb = s_lbub[seg];
+                    if (bb.x - bb.y == 0.0f) {
+                        lv[0] = lv[1] = lv[2] = lv[3] = 0;
+                    } else {
+                        const float den = __fsub_rn(bb.y, bb.x);
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            const float scaled = fabsf(__fdiv_rn(__fsub_rn(x[t], bb.x), den)) * s;
+                            const float cl = fminf(fmaxf(scaled, 0.0f), s - 1.0f);
+                            int li = (int)cl;
+                            if (random) li += (__fsub_rn(scaled, (float)li) > r[t]) ? 1 : 0;
+                            lv[t] = li;
+                        }
+                    }
+                } else {
+                    int sg = seg;
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const int i = i0 + t;
+                        if (i < n_chunks) {
+                            while (i >= s_seg[sg + 1]) ++sg;
+                            const float2 bb = s_lbub[sg];
+                            lv[t] = psc_level(x[t], bb.x, bb.y, s, random, r[t]);
+                        } else {
+                            lv[t] = 0;
+                        }
+                    }
+                }
+                const uint32_t packed = (uint32_t)lv[0] | ((uint32_t)lv[1] << 8) | ((uint32_t)lv[2] << 16) | ((uint32_t)lv[3] << 24);
+                if (i0 + 3 < n_chunks) {
+                    reinterpret_cast<uint32_t *>(P.l)[q] = packed;
+                } else {
+                    for (int t = 0; t < 4; ++t)
+                        if (i0 + t < n_chunks) P.l[i0 + t] = (uint8_t)lv[t];
+                }
+                if (R.n > 0) {   // the record sections are padded to 256 bytes: whole words may be written remotely
+                    remote_st32(R, reinterpret_cast<uint32_t *>(P.l) + q, packed);
+                    remote_st32(R, reinterpret_cast<uint32_t *>(P.codes) + q, cw[j]);
+                }
+            }
+        }
+    }
+    if (R.n > 0) {
+        // identity section (written by the riders of all CTAs before the grid barrier), then the
+        // delivery handshake: the last CTA to finish announces the epoch to every rank
+        const int64_t n16 = R.ident_bytes >> 4;
+        for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n16; i += (int64_t)gridDim.x * kThreads) {
+            const uint4 w = __ldcg(reinterpret_cast<const uint4 *>(R.ident) + i);
+            remote_st128(R, const_cast<uint8_t *>(R.ident) + 16 * i, w);
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t prev = atomicAdd(R.done, 1u);
+            s_misc[0] = (prev == gridDim.x - 1) ? 1 : 0;
+            __threadfence_system();
+        }
+        __syncthreads();
+        if (s_misc[0] && (int)threadIdx.x < R.n_flag)
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(R.flag[threadIdx.x]), "r"(R.epoch) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------ host side ---
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+static int make_map(CUtensorMap *map, const float *base, int64_t rows)
+{
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return GQ_ERR_CUDA;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)kD, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)kD * 4};
+    cuuint32_t box[2] = {(cuuint32_t)kD, (cuuint32_t)kTileM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (base %p, rows %lld)", (int)r, (const void *)base,
+                  (long long)rows);
+        return GQ_ERR_CUDA;
+    }
+    return GQ_OK;
+}
+
+struct Variant {
+    int groups;
+    bool pair, fmask, f2;
+};
+
+// GQ_TC2 = comma-separated switches, read at every launch (A/B runs): g3 | g4, pair, nopair, fmask,
+// nofmask, f2, nof2
+static Variant pick_variant()
+{
+    Variant v = {3, true, true, true};
+    if (const char *e = getenv("GQ_TC2")) {
+        if (strstr(e, "g4")) v.groups = 4;
+        if (strstr(e, "g3")) v.groups = 3;
+        if (strstr(e, "nopair")) v.pair = false; else if (strstr(e, "pair")) v.pair = true;
+        if (strstr(e, "nofmask")) v.fmask = false; else if (strstr(e, "fmask")) v.fmask = true;
+        if (strstr(e, "nof2")) v.f2 = false; else if (strstr(e, "f2")) v.f2 = true;
+    }
+    return v;
+}
+
+template <int G, bool PAIR, bool FMASK, bool F2>
+static int launch_one(const CUtensorMap &mg, const Enc2 &P, int grid, cudaStream_t st)
+{
+    auto kern = hsq_encode_tc2_kernel<G, PAIR, FMASK, F2>;
+    static bool attr_set = false;   // per instantiation
+    if (!attr_set) {
+        GQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Layout<G>::kSmemBytes));
+        attr_set = true;
+    }
+    GQ_CUDA(launch_pdl(kern, dim3(grid), dim3(128 + 128 * G), (size_t)Layout<G>::kSmemBytes, st, mg, P));
+    return GQ_OK;
+}
+
+template <int G>
+static int launch_g(const Variant &v, const CUtensorMap &mg, const Enc2 &P, int grid, cudaStream_t st)
+{
+    const int sel = (v.pair ? 4 : 0) | (v.fmask ? 2 : 0) | (v.f2 ? 1 : 0);
+    switch (sel) {
+    case 0: return launch_one<G, false, false, false>(mg, P, grid, st);
+    case 1: return launch_one<G, false, false, true>(mg, P, grid, st);
+    case 2: return launch_one<G, false, true, false>(mg, P, grid, st);
+    case 3: return launch_one<G, false, true, true>(mg, P, grid, st);
+    case 4: return launch_one<G, true, false, false>(mg, P, grid, st);
+    case 5: return launch_one<G, true, false, true>(mg, P, grid, st);
+    case 6: return launch_one<G, true, true, false>(mg, P, grid, st);
+    default: return launch_one<G, true, true, true>(mg, P, grid, st);
+    }
+}
+
+}  // namespace tc2
+
+bool hsq_tc2_tail_supported(int n_seg, int n_bit, int l_bytes, const void *u_out, const void *uniforms, const void *l,
+                            const void *codes)
+{
+    return n_seg <= tc2::kTailMaxSeg && n_bit >= 1 && n_bit <= 7 && l_bytes == 1 && ((uintptr_t)u_out & 15) == 0 &&
+           ((uintptr_t)uniforms & 15) == 0 && ((uintptr_t)l & 3) == 0 && ((uintptr_t)codes & 3) == 0;
+}
+
+// One-launch encode (or search only when tail == nullptr).  keys == nullptr: no min/max.  flag: 8-byte
+// scratch word for the in-kernel key reset; barrier: 2 x uint32 scratch (grid barrier, delivery counter).
+int hsq_encode_tc2(const float *grad, int64_t n_chunks, const float *codebook, void *codes, float *u_out,
+                   const int64_t *seg_start, int n_seg, uint32_t *keys, uint64_t *flag, uint32_t *barrier,
+                   const Rider &rider, const Tc2Tail *tail, const Tc2Remote *remote, cudaStream_t st)
+{
+    using namespace tc2;
+    GQ_REQUIRE(((uintptr_t)grad & 15) == 0 && ((uintptr_t)codebook & 15) == 0, "TMA needs 16-byte aligned bases");
+    GQ_REQUIRE(n_chunks > 0 && n_chunks < ((int64_t)1 << 31) - 256, "n_chunks out of range for one tensor map");
+    CUtensorMap mg;
+    int e = make_map(&mg, grad, n_chunks);
+    if (e) return e;
+    static std::atomic<unsigned long long> counter{[] {
+        unsigned long long seed = (unsigned long long)(uintptr_t)&seed ^ (unsigned long long)clock();
+        seed = seed * 6364136223846793005ull + 1442695040888963407ull;
+        return (seed >> 16) << 32;
+    }()};
+    Enc2 P = {};
+    P.codebook = codebook;
+    P.n_chunks = (int)n_chunks;
+    P.codes = (uint8_t *)codes;
+    P.u_out = u_out;
+    P.seg_start = seg_start;
+    P.n_seg = n_seg;
+    P.keys = keys;
+    P.flag = keys ? reinterpret_cast<unsigned long long *>(flag) : nullptr;
+    P.id = counter.fetch_add(1) + 1;
+    P.rider = rider;
+    if (tail != nullptr) {
+        GQ_REQUIRE(keys && flag && barrier, "the fused tail needs keys, flag and barrier scratch");
+        P.l = tail->l;
+        P.lbub = tail->lbub;
+        P.barrier = barrier;
+        P.uniforms = tail->uniforms;
+        P.seed = tail->seed;
+        P.offset = tail->offset;
+        P.s = (float)(1u << tail->n_bit);
+        P.random = tail->random;
+        if (remote != nullptr && remote->n > 0) {
+            Remote &R = P.remote;
+            R.n = remote->n;
+            R.multicast = remote->multicast;
+            for (int i = 0; i < 7; ++i) R.delta[i] = i < remote->n ? remote->delta[i] : 0;
+            R.ident = remote->ident;
+            R.ident_bytes = remote->ident_bytes;
+            R.done = barrier + 1;
+            R.n_flag = remote->n_flag;
+            for (int i = 0; i < 8; ++i) R.flag[i] = i < remote->n_flag ? remote->flag[i] : nullptr;
+            R.epoch = remote->epoch;
+        }
+    }
+    const int n_tiles = (int)((n_chunks + kTileM - 1) / kTileM);
+    int sms = sm_count();
+    if (const char *g = getenv("GQ_TC_GRID")) {
+        int v = atoi(g);
+        if (v > 0 && v < sms) sms = v;
+    }
+    const int grid = n_tiles < sms ? n_tiles : sms;
+    const Variant v = pick_variant();
+    e = (v.groups == 4) ? launch_g<4>(v, mg, P, grid, st) : launch_g<3>(v, mg, P, grid, st);
+    if (e) return e;
+    GQ_LAUNCH_CHECK("hsq_encode_tc2");
+    return GQ_OK;
+}
+
+}  // namespace gq
