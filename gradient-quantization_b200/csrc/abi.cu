@@ -136,6 +136,14 @@ int gq_hsq_search(const float *grad, int64_t n_chunks, int d, const float *codeb
                             minmax_keys, st);
 }
 
+int gq_hsq_tc2_trace(const float *grad, int64_t n_chunks, const float *codebook, void *codes, float *u_out,
+                     int64_t *trace, gq_stream_t stream)
+{
+    GQ_REQUIRE(hsq_tc_supported(16, 256, 1), "tcgen05 search needs an sm_100 device");
+    return hsq_search_tc2_trace(grad, n_chunks, codebook, codes, u_out, reinterpret_cast<long long *>(trace),
+                                as_stream(stream));
+}
+
 int gq_norm_quantize(const float *u, int64_t n, const int64_t *seg_start, int n_seg, int n_bit,
                      int random, const float *uniforms, uint64_t philox_seed, uint64_t philox_offset,
                      void *l, int l_bytes, float *lbub, uint32_t *minmax_keys, int precomputed,

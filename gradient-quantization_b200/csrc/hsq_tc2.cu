@@ -95,6 +95,7 @@ struct Enc2 {
     float s;
     int random;
     Remote remote;
+    long long *trace;            // TRACE builds only
 };
 
 __device__ __forceinline__ float4 lds_f4(uint32_t a)
@@ -161,10 +162,15 @@ __device__ __forceinline__ void remote_st128(const Remote &R, void *local, uint4
     }
 }
 
-template <int G, bool PAIR, bool FMASK, bool F2>
+// TRACE builds: CTA 0 time-stamps pipeline events of its first 128 tiles, trace[event * 128 + it] =
+// clock64(): 0 TMA issued, 1 MMA issued, 2 accumulators seen by the epilogue warp, 3 TMEM released
+// (first pass done), 4 smem stage released, 5 candidate mask done, 6 rescoring done, 7 tile done,
+// 8 rescoring iterations of the warp (count, not a time); taken by quadrant 0 / lane 0 of each group.
+template <int G, bool PAIR, bool FMASK, bool F2, bool TRACE = false>
 __global__ void __launch_bounds__(128 + 128 * G, 1)
 hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_constant__ Enc2 P)
 {
+#define GQ_TRACE(ev, it_) do { if (TRACE && blockIdx.x == 0 && (it_) < 128) P.trace[(ev) * 128 + (it_)] = clock64(); } while (0)
     using L = Layout<G>;
     constexpr int kThreads = 128 + 128 * G;
     constexpr int kStages = L::kStages;
@@ -293,6 +299,7 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
                 mbar_wait_sleep(bar_empty + 8 * s, ((it / kStages) & 1) ^ 1);
                 mbar_expect_tx(bar_full + 8 * s, kTileBytes);
                 tma_load_2d(smem_u32(s_a + s * kTileBytes), &map_grad, bar_full + 8 * s, 0, (tile0 + it) * kTileM);
+                GQ_TRACE(0, it);
             }
         }
     } else if (warp == 1) {
@@ -310,6 +317,7 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
                 mma_tf32(taddr, adesc, bdesc, 0u, kIdesc);
                 mma_tf32(taddr, adesc + 2, bdesc + 2, 1u, kIdesc);
                 mma_commit(bar_tfull + 8 * s);
+                GQ_TRACE(1, it);
             }
         }
     } else if (warp < 4) {
@@ -357,6 +365,8 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
             mbar_wait_sleep(bar_tfull + 8 * s, ph);   // accumulators complete
             __syncwarp();
             tc_fence_after();
+            const bool tracer = TRACE && quad == 0 && lane == 0;
+            if (tracer) GQ_TRACE(2, it);
 
             // ---- pass over the 256 approximate scores of this row: maximum per group of 4 codewords
             //      (PAIR: doubled values, |p| + |m| per codeword pair)
@@ -400,6 +410,7 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * s);
+            if (tracer) GQ_TRACE(3, it);
 
             // ---- this row's chunk, from the (swizzled) smem tile
             float v[kD];
@@ -418,6 +429,7 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
             // release the smem stage only after EVERY lane's loads of v have returned (see hsq_tc.cu)
             const uint32_t all_loaded = __ballot_sync(0xffffffffu, !(n2 < 0.0f));   // always all ones
             if (lane == 0) mbar_arrive(bar_empty + 8 * s + ((all_loaded == 0u) ? 8u : 0u));
+            if (tracer) GQ_TRACE(4, it);
 
             // ---- row maximum (four chains of FMNMX3) and threshold
             float am[4];
@@ -473,7 +485,12 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
                 chi = zero ? 0u : 0xffffffffu;
             }
 
+            if (TRACE) {
+                __syncwarp();
+                if (tracer) GQ_TRACE(5, it);
+            }
             // ---- exact rescoring of the candidate groups
+            int n_iter = 0;
             int best_bits = -1, best_k = 0;
             float best_u = 0.0f;
             unsigned long long vv[F2 ? kD : 1];
@@ -536,8 +553,16 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
                     }
                 }
                 if (cur == 0u) { cur = nxt; nxt = 0u; gbase = 32; }
+                if (TRACE) ++n_iter;
             }
             __syncwarp();
+            if (TRACE) {
+                n_iter = (int)__reduce_max_sync(0xffffffffu, (unsigned)n_iter);
+                if (tracer) {
+                    GQ_TRACE(6, it);
+                    if (blockIdx.x == 0 && it < 128) P.trace[8 * 128 + it] = n_iter;
+                }
+            }
             if (valid) {
                 P.codes[c] = (uint8_t)best_k;
                 P.u_out[c] = best_u;
@@ -557,6 +582,7 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
                 const int seg = valid ? cached_segment(segc, P.seg_start, P.n_seg, (int64_t)c) : -1;
                 minmax_add_warp(mm, valid, seg, best_u, P.keys);
             }
+            if (tracer) GQ_TRACE(7, it);
         }
         if (P.keys != nullptr) minmax_flush_warp(mm, P.keys);
     }
@@ -822,6 +848,42 @@ static int launch_g(const Variant &v, const CUtensorMap &mg, const Enc2 &P, int 
 }
 
 }  // namespace tc2
+
+// search only, default variant, with the pipeline trace of CTA 0 (9 x 128 int64, device)
+int hsq_search_tc2_trace(const float *grad, int64_t n_chunks, const float *codebook, void *codes, float *u_out,
+                         long long *trace, cudaStream_t st)
+{
+    using namespace tc2;
+    GQ_REQUIRE(((uintptr_t)grad & 15) == 0 && ((uintptr_t)codebook & 15) == 0, "TMA needs 16-byte aligned bases");
+    GQ_REQUIRE(n_chunks > 0 && n_chunks < ((int64_t)1 << 31) - 256 && trace, "bad arguments");
+    CUtensorMap mg;
+    int e = make_map(&mg, grad, n_chunks);
+    if (e) return e;
+    Enc2 P = {};
+    P.codebook = codebook;
+    P.n_chunks = (int)n_chunks;
+    P.codes = (uint8_t *)codes;
+    P.u_out = u_out;
+    P.trace = trace;
+    const int n_tiles = (int)((n_chunks + kTileM - 1) / kTileM);
+    int sms = sm_count();
+    if (const char *g = getenv("GQ_TC_GRID")) {
+        int v = atoi(g);
+        if (v > 0 && v < sms) sms = v;
+    }
+    const int grid = n_tiles < sms ? n_tiles : sms;
+    const Variant v = pick_variant();
+    auto launch = [&](auto kern, int threads, size_t smem) -> int {
+        GQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GQ_CUDA(launch_pdl(kern, dim3(grid), dim3(threads), smem, st, mg, P));
+        return GQ_OK;
+    };
+    if (v.pair) e = launch(hsq_encode_tc2_kernel<3, true, true, true, true>, 512, Layout<3>::kSmemBytes);
+    else e = launch(hsq_encode_tc2_kernel<3, false, false, false, true>, 512, Layout<3>::kSmemBytes);
+    if (e) return e;
+    GQ_LAUNCH_CHECK("hsq_search_tc2_trace");
+    return GQ_OK;
+}
 
 bool hsq_tc2_tail_supported(int n_seg, int n_bit, int l_bytes, const void *u_out, const void *uniforms, const void *l,
                             const void *codes)

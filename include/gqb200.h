@@ -236,6 +236,12 @@ int gq_hsq_tc_debug(const float *grad, int64_t n_chunks, const float *codebook, 
                     float *u_out, const int64_t *seg_start, int n_seg, float *dbg_scores,
                     int dbg_tiles, gq_stream_t stream);
 
+/* Diagnostic hook for the second-generation tcgen05 kernel: search only, and CTA 0 time-stamps
+ * the pipeline events of its first 128 tiles into trace (device int64 [9 * 128], clock64 values;
+ * event list in hsq_tc2.cu).  How tests/tc2_trace.py measures where a tile's time goes. */
+int gq_hsq_tc2_trace(const float *grad, int64_t n_chunks, const float *codebook, void *codes,
+                     float *u_out, int64_t *trace, gq_stream_t stream);
+
 /* ------------------------------------------------------------------------- */
 /* Peer-to-peer exchange of packed records (one user per GPU on one NVLink/NVSwitch node).
  * Replaces the exchange step of PSQuantizer (quantizers/ps_quantizer.py:44-48, a Python list

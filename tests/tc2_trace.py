@@ -1,0 +1,56 @@
+#!/usr/bin/env python
+"""Pipeline trace of the second-generation tcgen05 search kernel (CTA 0, first 128 tiles).
+
+    python tests/tc2_trace.py [variant]      (GQ_TC2 switch string, default pair,fmask,f2)
+
+Prints, per epilogue group and averaged over the steady-state tiles, how many cycles a tile spends in
+each phase -- the evidence behind DESIGN.md's statement of what bounds the kernel."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+if len(sys.argv) > 1:
+    os.environ["GQ_TC2"] = sys.argv[1]
+os.environ["GQ_TC_V"] = "2"
+import gq_b200  # noqa: E402,F401
+from gq_b200 import _lib  # noqa: E402
+from util import codebook  # noqa: E402
+
+dev = torch.device("cuda", 0)
+cbt = torch.from_numpy(codebook(16, 256)).to(dev)
+n = 1468652
+xs = [torch.randn(n * 16, device=dev) * 0.01 for _ in range(3)]
+codes = torch.empty(n, dtype=torch.uint8, device=dev)
+u = torch.empty(n, device=dev)
+trace = torch.zeros(9 * 128, dtype=torch.int64, device=dev)
+for i in range(3):
+    _lib.call("gq_hsq_tc2_trace", xs[i].data_ptr(), n, cbt.data_ptr(), codes.data_ptr(), u.data_ptr(), trace.data_ptr(),
+              _lib.stream())
+torch.cuda.synchronize()
+t = trace.cpu().numpy().reshape(9, 128).astype(np.int64)
+tiles = 77
+t0 = t[0, 0]
+ev = (t[:8, :tiles] - t0)
+names = ["tma", "mma", "acc seen", "tmem rel", "stage rel", "mask done", "rescored", "done"]
+print("first 12 tiles (cycles since the first TMA):")
+for it in range(12):
+    print("  tile %2d: " % it + "  ".join("%s %6d" % (nm, ev[k, it]) for k, nm in enumerate(names)) + "  iters %d" % t[8, it])
+lo, hi = 9, tiles - 3
+sl = slice(lo, hi)
+print("steady state (tiles %d..%d), mean cycles:" % (lo, hi - 1))
+print("  tile period (done[i+3] - done[i]) / 3 : %.0f" % np.mean((ev[7, lo + 3:hi + 3] - ev[7, lo:hi]) / 3.0))
+print("  wait for accumulators (acc seen - previous tile of the group done): %.0f" % np.mean(ev[2, lo + 3:hi + 3] - ev[7, lo:hi]))
+print("  first pass  (tmem rel - acc seen) : %.0f" % np.mean(ev[3, sl] - ev[2, sl]))
+print("  v + norm    (stage rel - tmem rel): %.0f" % np.mean(ev[4, sl] - ev[3, sl]))
+print("  max + mask  (mask done - stage rel): %.0f" % np.mean(ev[5, sl] - ev[4, sl]))
+print("  rescoring   (rescored - mask done): %.0f   iterations %.2f" % (np.mean(ev[6, sl] - ev[5, sl]), np.mean(t[8, sl])))
+print("  store/minmax (done - rescored)    : %.0f" % np.mean(ev[7, sl] - ev[6, sl]))
+print("  MMA issue -> accumulators seen    : %.0f" % np.mean(ev[2, sl] - ev[1, sl]))
+print("  TMEM release(i) -> MMA issue(i+2) : %.0f" % np.mean(ev[1, lo + 2:hi + 2] - ev[3, lo:hi]))
+print("  TMA issue -> MMA issue            : %.0f" % np.mean(ev[1, sl] - ev[0, sl]))
+print("  total for the CTA: %d cycles for %d tiles" % (ev[7, tiles - 1], tiles))
