@@ -162,6 +162,15 @@ __device__ __forceinline__ void remote_st128(const Remote &R, void *local, uint4
     }
 }
 
+// the two K = 8 steps of one 128 x 256 x 16 tile product, then the commit that arrives on `bar`
+__device__ __forceinline__ void issue_tile_mma(uint32_t a_addr, uint32_t b_addr, uint32_t taddr, uint32_t bar)
+{
+    const uint64_t adesc = make_desc(a_addr), bdesc = make_desc(b_addr);
+    mma_tf32(taddr, adesc, bdesc, 0u, kIdesc);           // k = 0..7   (bytes  0..31 of each row)
+    mma_tf32(taddr, adesc + 2, bdesc + 2, 1u, kIdesc);   // k = 8..15  (bytes 32..63): +32 B = +2 units
+    mma_commit(bar);
+}
+
 // TRACE builds: CTA 0 time-stamps pipeline events of its first 128 tiles, trace[event * 128 + it] =
 // clock64(): 0 TMA issued, 1 MMA issued, 2 accumulators seen by the epilogue warp, 3 TMEM released
 // (first pass done), 4 smem stage released, 5 candidate mask done, 6 rescoring done, 7 tile done,
@@ -184,11 +193,11 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
     const uint32_t bar_full = smem_u32(bars);
     const uint32_t bar_empty = bar_full + 8 * kStages;
     const uint32_t bar_tfull = bar_empty + 8 * kStages;
-    const uint32_t bar_tempty = bar_tfull + 8 * kStages;
+    uint32_t *s_rel = reinterpret_cast<uint32_t *>(smem + L::kOffBar + 8 * (3 * kStages));   // [2] first-pass arrivals per TMEM buffer
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(smem + L::kOffBar + 8 * (4 * kStages));
     float *s_cn = reinterpret_cast<float *>(smem + L::kOffBar + 8 * (4 * kStages) + 8);   // [8] per-warp norm maxima
     int *s_misc = reinterpret_cast<int *>(smem + L::kOffBar + 8 * (4 * kStages) + 8 + 32);
-    static_assert(8 * (4 * kStages) + 8 + 32 + 16 <= 512, "barrier region");
+    static_assert(8 * (4 * kStages) + 8 + 32 + 16 <= 512 && 8 * (3 * kStages) + 8 <= 8 * (4 * kStages), "barrier region");
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -203,8 +212,9 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
             mbar_init(bar_full + 8 * s, 1);
             mbar_init(bar_empty + 8 * s, 4);
             mbar_init(bar_tfull + 8 * s, 1);
-            mbar_init(bar_tempty + 8 * s, 4);
         }
+        s_rel[0] = 0u;
+        s_rel[1] = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -304,19 +314,17 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
         }
     } else if (warp == 1) {
         // -------------------------------------------------------- MMA issuer ---
+        // Only the first two tiles are issued here.  Afterwards the MMA of local tile it + 2 is issued by
+        // whichever epilogue warp is the LAST of its group to finish reading TMEM buffer it & 1 (arrival
+        // counter in shared memory): a dedicated issuer warp sleeping on an mbarrier took ~1000 cycles
+        // from the release to the issue, and that turnaround (first pass + release -> issue -> accumulators
+        // seen), not the epilogue arithmetic, set the tile period (tests/tc2_trace.py).
         if (lane == 0) {
-            const uint64_t bdesc = make_desc(smem_u32(s_cb));
-            for (int it = 0; it < my_tiles; ++it) {
-                const int s = it % kStages;
-                const int b = it & 1;
-                if (it >= 2) mbar_wait_sleep(bar_tempty + 8 * ((it - 2) % kStages), ((it - 2) / kStages) & 1);
-                mbar_wait_sleep(bar_full + 8 * s, (it / kStages) & 1);
+            for (int it = 0; it < my_tiles && it < 2; ++it) {
+                mbar_wait_sleep(bar_full + 8 * it, 0);
                 tc_fence_after();
-                const uint64_t adesc = make_desc(smem_u32(s_a + s * kTileBytes));
-                const uint32_t taddr = tmem_base + (uint32_t)(b * kK);
-                mma_tf32(taddr, adesc, bdesc, 0u, kIdesc);
-                mma_tf32(taddr, adesc + 2, bdesc + 2, 1u, kIdesc);
-                mma_commit(bar_tfull + 8 * s);
+                issue_tile_mma(smem_u32(s_a + it * kTileBytes), smem_u32(s_cb), tmem_base + (uint32_t)(it * kK),
+                               bar_tfull + 8 * it);
                 GQ_TRACE(1, it);
             }
         }
@@ -406,10 +414,24 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
                     if (h + 1 < kK / 32) tmem_ld_wait16(sa);
                 }
             }
-            // TMEM buffer b may be overwritten by the MMA of local tile it + 2
+            // TMEM buffer b may be overwritten by the MMA of local tile it + 2: the last of the group's four
+            // warps to get here issues it (acq_rel counter: the other warps' TMEM loads happen before it)
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tempty + 8 * s);
+            if (lane == 0) {
+                uint32_t old;
+                asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(s_rel + b)) : "memory");
+                const int nt = it + 2;
+                if ((old & 3u) == 3u && nt < my_tiles) {
+                    const int ns = nt % kStages;
+                    mbar_wait(bar_full + 8 * ns, (nt / kStages) & 1);   // the TMA ring runs several tiles ahead
+                    tc_fence_after();
+                    issue_tile_mma(smem_u32(s_a + ns * kTileBytes), smem_u32(s_cb), tmem_base + (uint32_t)(b * kK),
+                                   bar_tfull + 8 * ns);
+                    GQ_TRACE(1, nt);
+                }
+            }
+            __syncwarp();
             if (tracer) GQ_TRACE(3, it);
 
             // ---- this row's chunk, from the (swizzled) smem tile
