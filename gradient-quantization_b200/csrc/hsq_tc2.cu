@@ -415,12 +415,14 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
                 }
             }
             // TMEM buffer b may be overwritten by the MMA of local tile it + 2: the last of the group's four
-            // warps to get here issues it (acq_rel counter: the other warps' TMEM loads happen before it)
+            // warps to get here issues it.  The counter is a RELAXED shared-memory atomic: every warp's TMEM
+            // loads have completed (tcgen05.wait::ld) before its increment is issued, and the tcgen05
+            // before/after_thread_sync fences order the asynchronous tensor-core accesses around it; an
+            // acq_rel atomic costs a MEMBAR that waits for the previous tile's global stores (+700 cycles).
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-                uint32_t old;
-                asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(s_rel + b)) : "memory");
+                const uint32_t old = atomicAdd(s_rel + b, 1u);
                 const int nt = it + 2;
                 if ((old & 3u) == 3u && nt < my_tiles) {
                     const int ns = nt % kStages;
