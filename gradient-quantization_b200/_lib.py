@@ -48,6 +48,8 @@ _SIGNATURES = {
     "gq_peer_gather": (c_int, [c_void_p, c_void_p, c_size, c_size, c_int, c_void_p]),
     "gq_peer_push": (c_int, [c_void_p, c_void_p, c_size, c_int, c_void_p]),
     "gq_peer_push_multicast": (c_int, [c_void_p, c_void_p, c_size, c_void_p]),
+    "gq_attach_remote_record": (c_int, [c_int, c_int, c_void_p, c_void_p, c_i64, c_void_p, c_int, ctypes.c_uint32]),
+    "gq_attach_peer_wait": (c_int, [c_void_p, c_int, ctypes.c_uint32]),
     "gq_f32_reduce_users": (c_int, [c_void_p, c_i64, c_int, c_i64, c_int, c_int, c_void_p, c_void_p]),
     "gq_qsgd_wire_bits": (c_int, [c_int]),
     "gq_qsgd_encode": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_int, c_int, c_int, c_void_p, c_u64,
@@ -68,6 +70,7 @@ _SIGNATURES = {
     "gq_hsq_tc_debug": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
                                 c_int, c_void_p]),
     "gq_hsq_tc2_trace": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "gq_gather_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "gq_axpy": (c_int, [c_void_p, c_void_p, c_float, c_i64, c_void_p, c_void_p]),
     "gq_sub": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_void_p]),
     "gq_hsq_host_scratch_bytes": (c_size, [c_i64, c_int, c_int, c_int]),
@@ -140,18 +143,60 @@ def f32c(t, what="tensor"):
     return t if t.is_contiguous() else t.contiguous()
 
 
-class PhiloxState:
-    """Seed/offset bookkeeping for the on-device Philox stream.  The state is torch's
-    own CUDA generator: the seed follows torch.manual_seed, the offset is read from and
-    advanced on torch.cuda.default_generators[device], so torch.manual_seed(s) replays
-    the same draws and interleaved torch.rand(device='cuda') calls never reuse them."""
+_M64 = 0xFFFFFFFFFFFFFFFF
 
-    def take(self, n):
-        gen = torch.cuda.default_generators[torch.cuda.current_device()]
-        seed = gen.initial_seed() & 0xFFFFFFFFFFFFFFFF
+
+def _mix64(seed, k):
+    """SplitMix64 finaliser of (seed, k): statistically independent Philox keys per logical stream."""
+    z = (seed + (k + 1) * 0x9E3779B97F4A7C15) & _M64
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _M64
+    return z ^ (z >> 31)
+
+
+class PhiloxState:
+    """Seed/offset bookkeeping for the on-device Philox stream.
+
+    take(n, user): the stochastic-rounding draws of one simulated user's record().  The Philox key is
+    mix(seed, user) -- with one user per rank and the usual identical torch.manual_seed on every rank
+    (main.py:127) the users still draw INDEPENDENT uniforms, like the reference's single CPU stream
+    does; the offset is read from and advanced on torch's CUDA generator of the current device, so
+    torch.manual_seed(s) replays the same draws and interleaved torch.rand(device='cuda') calls never
+    reuse them.
+
+    take_shared(n): draws that every rank must reproduce identically (the second compression of
+    --two-phase, ps_quantizer.py:52-61): key mix(shared seed, 2^32), own offset counter advanced only
+    here, both independent of the rank's generator state.  The shared seed is the generator seed of
+    rank 0 (share_seed(), broadcast once by the quantizer) or the local one in a single process."""
+
+    SHARED_STREAM = 1 << 32
+
+    def __init__(self):
+        self.shared_seed = None
+        self.shared_offset = 0
+
+    def _gen(self):
+        return torch.cuda.default_generators[torch.cuda.current_device()]
+
+    def take(self, n, user=0):
+        gen = self._gen()
+        seed = gen.initial_seed() & _M64
         off = int(gen.get_offset())
         gen.set_offset(off + (int(n) + 3) // 4 * 4)
-        return seed, off
+        return _mix64(seed, int(user)), off
+
+    def share_seed(self, seed=None):
+        """Fix the seed of the rank-independent stream (None: this process's generator seed)."""
+        self.shared_seed = (self._gen().initial_seed() if seed is None else int(seed)) & _M64
+        self.shared_offset = 0
+        return self.shared_seed
+
+    def take_shared(self, n):
+        if self.shared_seed is None:
+            self.share_seed()
+        off = self.shared_offset
+        self.shared_offset = off + (int(n) + 3) // 4 * 4
+        return _mix64(self.shared_seed, self.SHARED_STREAM), off
 
 
 PHILOX = PhiloxState()

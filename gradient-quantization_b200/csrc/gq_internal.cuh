@@ -97,6 +97,36 @@ int hsq_search_tc2_trace(const float *grad, int64_t n_chunks, const float *codeb
 Tc2Remote take_remote();
 void set_remote(const Tc2Remote &r);
 
+// Wait (inside the next decode kernel, or a one-warp kernel of its own) until every rank has
+// announced `epoch` in this rank's flag array: the receiving side of the fused peer-to-peer push.
+struct PeerWait {
+    const uint32_t *flags;   // local flag array, flags[r] = last epoch rank r has delivered
+    int n;                   // ranks (0: nothing to wait for)
+    uint32_t epoch;
+    unsigned long long timeout_ns;
+};
+void set_wait(const PeerWait &w);
+PeerWait take_wait();
+int flush_wait(cudaStream_t st);
+// bounded by wall clock (not by a poll count): rank skew of seconds is normal in training (evaluation
+// or a checkpoint on one rank), minutes are not; on timeout the kernel traps (sticky error on this rank)
+__device__ __forceinline__ void peer_wait_flag(const uint32_t *flag, uint32_t epoch, unsigned long long timeout_ns)
+{
+    unsigned long long t0 = 0ull;
+    for (;;) {
+        uint32_t seen;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
+        if ((int32_t)(seen - epoch) >= 0) return;
+        __nanosleep(64);
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0ull) t0 = now;
+        else if (now - t0 > timeout_ns) __trap();
+    }
+}
+unsigned long long peer_timeout_ns();   // p2p.cu
+#define GQ_CUDA_INT(expr) do { int _e2 = (expr); if (_e2) return _e2; } while (0)
+
 // hsq_tail.cu
 int launch_seg_minmax(const float *u, int64_t n, const int64_t *seg_start, int n_seg, uint32_t *keys,
                       cudaStream_t st);

@@ -579,7 +579,7 @@ hsq_decode_reduce_staged_kernel(const uint8_t *__restrict__ codes, const uint8_t
                                 const float *__restrict__ lbub, const UserOffsets uoff,
                                 int64_t n_chunks, const float *__restrict__ codebook,
                                 const int64_t *__restrict__ seg_start, int n_seg, float s, int mean,
-                                int accumulate, float *__restrict__ out, const Rider rider)
+                                int accumulate, float *__restrict__ out, const Rider rider, const PeerWait wait)
 {
     extern __shared__ float4 s_dyn[];
     float4 *s_cb = s_dyn;                                                    // [256][2][4]
@@ -599,6 +599,10 @@ hsq_decode_reduce_staged_kernel(const uint8_t *__restrict__ codes, const uint8_t
         s_cb[i] = __ldg(reinterpret_cast<const float4 *>(codebook) + (i >> 3) * 4 + (i & 3));
     __syncthreads();
     pdl_wait();   // the records are complete (and, across GPUs, announced by the barrier kernel)
+    if (wait.n > 0) {   // ... or by the peers' encode kernels themselves: wait for every rank's delivery flag
+        if (tid < wait.n) peer_wait_flag(wait.flags + tid, wait.epoch, wait.timeout_ns);
+        __syncthreads();
+    }
     const int64_t n_tiles = (n_chunks + kStTile - 1) / kStTile;
     auto issue = [&](int64_t tile, int buf) {
         const int64_t c0 = tile * kStTile;
@@ -756,9 +760,10 @@ static int launch_decode_staged(const void *codes, const void *l, const float *l
     int64_t grid = (n_tiles + per - 1) / per;
     if (grid < 1) grid = 1;
     const Rider rider = take_rider();   // carried by this launch if one is pending
+    const PeerWait wait = take_wait();  // likewise: the wait for the peers' delivery flags
     GQ_CUDA(launch_pdl(kern, dim3((unsigned)grid), dim3(kDecodeThreads), smem, st, (const uint8_t *)codes,
                        (const uint8_t *)l, lbub, uoff, n_chunks, codebook, seg_start, n_seg, s, mean,
-                       accumulate, out, rider));
+                       accumulate, out, rider, wait));
     return GQ_OK;
 }
 
@@ -818,6 +823,7 @@ static int launch_decode_d(const void *codes, const void *l, const float *lbub, 
 #undef GQ_S
             }
         }
+        GQ_CUDA_INT(flush_wait(st));
 #define GQ_W(MU) return launch_decode_warp<DW, MU, CodeT, LT>(codes, l, lbub, norms_f32, uoff, n_users, n_chunks, codebook, K, seg_start, n_seg, s, n_bit, mean, accumulate, out, st)
         if (n_users == 1) GQ_W(1);
         if (n_users == 2) GQ_W(2);
@@ -828,7 +834,9 @@ static int launch_decode_d(const void *codes, const void *l, const float *lbub, 
     if (user_offsets != nullptr) {
         set_error("scattered user records need chunk dim 4/8/16, a codebook <= 64 KB and <= 8 users");
         return GQ_ERR_UNSUPPORTED;
-    } else if (cb_bytes <= 64 * 1024) {
+    }
+    GQ_CUDA_INT(flush_wait(st));
+    if (cb_bytes <= 64 * 1024) {
         auto kern = hsq_decode_reduce_kernel<D, CodeT, LT, true>;
         GQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cb_bytes));
         // persistent: the codebook is staged once per CTA; exactly one resident wave
@@ -868,6 +876,7 @@ static int launch_decode(const void *codes, const void *l, const float *lbub, co
         return GQ_ERR_UNSUPPORTED;
     }
     const float s = (n_bit == 32) ? 1.0f : (float)(1u << n_bit);
+    GQ_CUDA_INT(flush_wait(st));
     hsq_decode_reduce_generic_kernel<CodeT, LT><<<grid_for(n_chunks * (int64_t)d, 256), 256, 0, st>>>(
         (const CodeT *)codes, (const LT *)l, lbub, norms_f32, user_stride, n_users, n_chunks, d,
         codebook, seg_start, n_seg, s, n_bit, mean, accumulate, out);
@@ -945,6 +954,29 @@ int launch_f32_reduce_users(const float *in, int64_t user_stride, const int64_t 
 }
 
 // ---------------------------------------------------------- attached reduction ---
+// ---- pending wait for the peers' delivery flags (fused peer-to-peer push) ----
+static thread_local PeerWait g_wait = {};
+void set_wait(const PeerWait &w) { g_wait = w; }
+PeerWait take_wait()
+{
+    PeerWait w = g_wait;
+    g_wait = PeerWait{};
+    return w;
+}
+__global__ void peer_wait_kernel(const PeerWait wait)
+{
+    pdl_launch_dependents();
+    pdl_wait();
+    if ((int)threadIdx.x < wait.n) peer_wait_flag(wait.flags + threadIdx.x, wait.epoch, wait.timeout_ns);
+}
+int flush_wait(cudaStream_t st)
+{
+    const PeerWait w = take_wait();
+    if (w.n <= 0) return GQ_OK;
+    GQ_CUDA(launch_pdl(peer_wait_kernel, dim3(1), dim3(32), 0, st, w));
+    return GQ_OK;
+}
+
 static thread_local Rider g_rider = {};
 
 void set_rider(const Rider &r) { g_rider = r; }

@@ -6,6 +6,7 @@
 // waits for theirs, and the fused decode-and-average kernel then pulls the 2/d bytes per element
 // of the other users straight out of peer HBM while it works.  Replaces the NCCL all-gather of
 // quantizers/ps_quantizer.py's exchange step (3 MB per rank: latency-, not bandwidth-bound).
+#include <stdlib.h>
 #include <string.h>
 
 #include "gq_internal.cuh"
@@ -20,20 +21,26 @@ struct PeerFlags {
 
 // flags layout on every rank: uint32 flags[8]; flags[r] = last epoch rank r has announced to me
 __global__ void peer_barrier_kernel(uint32_t *local_flags, const PeerFlags peers, int rank, int n_ranks,
-                                    uint32_t epoch)
+                                    uint32_t epoch, unsigned long long timeout_ns)
 {
     const int u = threadIdx.x;
     if (u < n_ranks) {
         // everything this GPU wrote before the kernel (its packed record) becomes visible to peer u
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peers.p[u] + rank), "r"(epoch) : "memory");
-        uint32_t seen, spins = 0;
-        do {
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(local_flags + u) : "memory");
-            if ((int32_t)(seen - epoch) >= 0) break;
-            __nanosleep(100);
-        } while (++spins < (1u << 26));
-        if ((int32_t)(seen - epoch) < 0) __trap();   // a peer never arrived: fail loudly, do not hang
+        peer_wait_flag(local_flags + u, epoch, timeout_ns);   // a peer never arrived: trap, do not hang
     }
+}
+
+// GQ_PEER_TIMEOUT_S (default 120): how long a rank waits for its peers before it traps
+unsigned long long peer_timeout_ns()
+{
+    static const unsigned long long ns = [] {
+        const char *e = getenv("GQ_PEER_TIMEOUT_S");
+        double s = e ? atof(e) : 120.0;
+        if (!(s > 0.0)) s = 120.0;
+        return (unsigned long long)(s * 1e9);
+    }();
+    return ns;
 }
 
 struct PeerPtrs {
@@ -155,7 +162,7 @@ int gq_peer_barrier(void *const *flag_ptrs, int rank, int n_ranks, uint32_t epoc
     GQ_REQUIRE(flag_ptrs && n_ranks >= 1 && n_ranks <= 8 && rank >= 0 && rank < n_ranks, "bad arguments");
     PeerFlags pf;
     for (int r = 0; r < 8; ++r) pf.p[r] = (r < n_ranks) ? reinterpret_cast<uint32_t *>(flag_ptrs[r]) : nullptr;
-    peer_barrier_kernel<<<1, 32, 0, as_stream(stream)>>>(pf.p[rank], pf, rank, n_ranks, epoch);
+    peer_barrier_kernel<<<1, 32, 0, as_stream(stream)>>>(pf.p[rank], pf, rank, n_ranks, epoch, peer_timeout_ns());
     GQ_LAUNCH_CHECK("peer_barrier");
     return GQ_OK;
 }
@@ -199,6 +206,51 @@ int gq_peer_push(const void *src, void *const *dst_ptrs, size_t bytes, int n_dst
     if (bx < 1) bx = 1;
     peer_push_kernel<<<bx, 256, 0, as_stream(stream)>>>(reinterpret_cast<const uint4 *>(src), pd, n_dst, n16);
     GQ_LAUNCH_CHECK("peer_push");
+    return GQ_OK;
+}
+
+// Fused exchange, sending side: the NEXT gq_hsq_encode on this host thread also stores every finished
+// section of the record it writes at (local address + delta[i]) for i < n_remote (peer-mapped copies of
+// the same record row), or once through an NVLS multicast mapping (multicast = 1, n_remote = 1), mirrors
+// the identity section [ident, ident + ident_bytes) the same way, and finally stores `epoch` into the
+// n_flags words flag_ptrs[i] (this rank's slot in every rank's flag array, its own included).
+// Requires the one-launch tcgen05 encode (d = 16, K = 256, uint8 codes and levels); otherwise that
+// encode fails with GQ_ERR_UNSUPPORTED and nothing is sent.
+int gq_attach_remote_record(int n_remote, int multicast, const int64_t *delta, const void *ident, int64_t ident_bytes,
+                            void *const *flag_ptrs, int n_flags, uint32_t epoch)
+{
+    GQ_REQUIRE(n_remote >= 1 && n_remote <= 7 && delta && flag_ptrs && n_flags >= 1 && n_flags <= 8, "bad arguments");
+    GQ_REQUIRE(!multicast || n_remote == 1, "a multicast delivery has one destination");
+    GQ_REQUIRE(ident_bytes >= 0 && ident_bytes % 16 == 0 && (ident_bytes == 0 || ((uintptr_t)ident & 15) == 0),
+               "identity section must be 16-byte granular");
+    Tc2Remote r = {};
+    r.n = n_remote;
+    r.multicast = multicast;
+    for (int i = 0; i < n_remote; ++i) {
+        GQ_REQUIRE(delta[i] % 16 == 0, "remote copies must keep the 16-byte alignment");
+        r.delta[i] = delta[i];
+    }
+    r.ident = reinterpret_cast<const uint8_t *>(ident);
+    r.ident_bytes = ident_bytes;
+    r.n_flag = n_flags;
+    for (int i = 0; i < n_flags; ++i) r.flag[i] = reinterpret_cast<uint32_t *>(flag_ptrs[i]);
+    r.epoch = epoch;
+    set_remote(r);
+    return GQ_OK;
+}
+
+// Fused exchange, receiving side: the NEXT HSQ decode on this host thread first waits until all
+// n_ranks words of the local flag array have reached `epoch` (inside the decode kernel's prologue
+// when it is the staged kernel, else in a one-warp kernel launched before it).
+int gq_attach_peer_wait(const void *local_flags, int n_ranks, uint32_t epoch)
+{
+    GQ_REQUIRE(local_flags && n_ranks >= 1 && n_ranks <= 8, "bad arguments");
+    PeerWait w = {};
+    w.flags = reinterpret_cast<const uint32_t *>(local_flags);
+    w.n = n_ranks;
+    w.epoch = epoch;
+    w.timeout_ns = peer_timeout_ns();
+    set_wait(w);
     return GQ_OK;
 }
 

@@ -219,15 +219,26 @@ class FusedPlan:
         return base if base % 256 == 0 else None
 
     def gather(self, tensors, buf=None):
-        """Copy per-parameter gradients into the arena (skips views already in it)."""
-        dst, src = [], []
+        """Copy per-parameter gradients into the arena (skips views already in it): one
+        multi-tensor kernel (gq_gather_f32), the pointer table travels as its parameter."""
+        import ctypes
+        buf = self.arena if buf is None else buf
+        base = buf.data_ptr()
+        ptrs, offs, sizes, keep = [], [], [], []
         for i, t in enumerate(tensors):
-            v = self.view(i, buf)
-            if t.data_ptr() != v.data_ptr():
-                dst.append(v)
-                src.append(t.detach().reshape(self.shapes[i]))
-        if dst:
-            torch._foreach_copy_(dst, src)
+            if t.data_ptr() == base + self.tensor_off[i] * 4:
+                continue
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                t = _lib.f32c(t.detach())
+                keep.append(t)            # alive until the launch below is queued (stream-ordered free)
+            _lib.require_cuda(t, "gradient")
+            ptrs.append(t.data_ptr())
+            offs.append(self.tensor_off[i])
+            sizes.append(self.sizes[i])
+        n = len(ptrs)
+        if n:
+            _lib.call("gq_gather_f32", (ctypes.c_void_p * n)(*ptrs), (ctypes.c_int64 * n)(*offs),
+                      (ctypes.c_int64 * n)(*sizes), n, base, _lib.stream())
 
     def compressed_elems(self):
         return sum(g.n for g in self.groups if g.kind != "identity")
@@ -279,13 +290,17 @@ class FusedPlan:
         return out, pos
 
     # --------------------------------------------------------------- encode ---
-    def encode(self, user, src=None, uniforms=None):
+    def encode(self, user, src=None, uniforms=None, rng_user=None, shared_rng=False):
         """Compress the arena (or `src`, laid out like it) into records[user].
+        rng_user: logical user whose Philox stream the stochastic rounding draws from (default: the
+        record row); shared_rng: the rank-independent stream instead (second phase of --two-phase).
         Launches: HSQ 2 per group on the tcgen05 path (search, quantize; 3 with the separate init
         kernel of the exact path), QSGD 3, sign 1, top-k 12; the copy of the identity tensors rides
         in the first HSQ group's first kernel (1 launch of its own when there is no HSQ group)."""
         src = self.arena if src is None else src
         src_ptr = src if isinstance(src, int) else src.data_ptr()   # tensor or raw device address
+        rng_user = user if rng_user is None else rng_user
+        take = _lib.PHILOX.take_shared if shared_rng else (lambda n: _lib.PHILOX.take(n, rng_user))
         rec = self.records[user]
         st = _lib.stream()
         base = rec.data_ptr()
@@ -298,7 +313,7 @@ class FusedPlan:
                           base + ident.raw_off)
             if g.kind == "hsq":
                 n_rand = g.n_chunks if (self.random and g.n_bit != 32) else 0
-                seed, off = _lib.PHILOX.take(n_rand) if (n_rand and r is None) else (0, 0)
+                seed, off = take(n_rand) if (n_rand and r is None) else (0, 0)
                 if g.n_bit == 32:
                     _lib.call("gq_hsq_encode", gp, g.n_chunks, g.dim, _lib.ptr(g.codebook), g.K,
                               _lib.ptr(g.seg_start), g.n_seg, 32, 0, None, 0, 0, base + g.codes_off,
@@ -311,7 +326,7 @@ class FusedPlan:
                               base + g.lbub_off, _lib.ptr(self.u_scratch), _lib.ptr(self.workspace),
                               self.workspace.numel(), self.algo, st)
             elif g.kind == "qsgd":
-                seed, off = _lib.PHILOX.take(g.n) if (self.random and r is None) else (0, 0)
+                seed, off = take(g.n) if (self.random and r is None) else (0, 0)
                 _lib.call("gq_qsgd_encode", gp, g.n, _lib.ptr(g.chunk_start), g.n_chunks, g.dim, g.n_bit,
                           self.random, _lib.ptr(r), seed, off, base + g.norm_off, None, None,
                           base + g.packed_off, st)
@@ -344,6 +359,19 @@ class FusedPlan:
             if g.kind != "hsq" or g.dim not in (4, 8, 16) or g.K * g.dim * 4 > 65536 or g.n_bit == 32:
                 return False
         return True
+
+    def supports_fused_delivery(self):
+        """The one-launch tcgen05 encode can deliver the record to the peers itself when the plan is a
+        single HSQ group of the headline shape (d = 16, K = 256, uint8 codes and levels) plus identity."""
+        import os
+        if os.environ.get("GQ_TC_V", "2") == "1" or self.algo == _lib.ALGO_EXACT:
+            return False
+        hsq = [g for g in self.groups if g.kind != "identity"]
+        if len(hsq) != 1 or hsq[0].kind != "hsq":
+            return False
+        g = hsq[0]
+        return (g.dim == 16 and g.K == 256 and g.code_bytes == 1 and g.n_bit <= 7 and g.l_bytes == 1
+                and g.n_seg <= 1024 and g.n_chunks > 0)
 
     def decode(self, first_user=0, n_users=None, mean=True, accumulate=False, out=None,
                base_ptr=None, user_offsets=None):
@@ -410,7 +438,11 @@ class FusedPlan:
                 k -= 2          # search only
             elif (g.kind == "hsq" and g.dim == 16 and g.K == 256 and g.code_bytes == 1
                   and self.algo != _lib.ALGO_EXACT):
-                k -= 1          # tcgen05 search resets the min/max keys itself: search + quantize
+                # tcgen05: the search kernel resets the min/max keys itself; second generation: the norm
+                # quantization is its fused tail as well (one launch)
+                import os
+                v1 = os.environ.get("GQ_TC_V", "2") == "1"
+                k -= 1 if (v1 or g.n_seg > 1024 or g.n_bit > 7) else 2
             n += k
         ident, carrier = self._rider_pair()
         if carrier is not None and carrier.n_bit != 32:   # the copy rides in the HSQ init / search kernel

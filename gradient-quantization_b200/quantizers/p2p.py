@@ -112,6 +112,29 @@ class PeerRecords:
     def parity(self):
         return self.step & 1
 
+    def attach_delivery(self, plan):
+        """Fused push: the next encode of `plan` into row `row()` also stores the record into the same
+        row of every peer's block (or once through the multicast mapping) and then announces the new
+        epoch in every rank's flag array (its own included)."""
+        self.epoch += 1
+        local = self._addr(self.rank, self.rank)
+        if self.mc_base:
+            deltas = [self.mc_base + self.row() * self.record_bytes - local]
+            mc = 1
+        else:
+            deltas = [self._addr(r, self.rank) - local for r in range(self.world) if r != self.rank]
+            mc = 0
+        ident = next((g for g in plan.groups if g.kind == "identity" and g.n), None)
+        ident_ptr = local + ident.raw_off if ident is not None else None
+        ident_bytes = (ident.n * 4 + 15) // 16 * 16 if ident is not None else 0
+        flags = (ctypes.c_void_p * self.world)(*[int(self._flag_ptrs[r]) + 4 * self.rank for r in range(self.world)])
+        _lib.call("gq_attach_remote_record", len(deltas), mc, (ctypes.c_int64 * len(deltas))(*deltas), ident_ptr,
+                  ident_bytes, ctypes.cast(flags, ctypes.c_void_p), self.world, self.epoch)
+
+    def attach_wait(self):
+        """Fused push, receiving side: the next decode waits for every rank's flag of this epoch."""
+        _lib.call("gq_attach_peer_wait", int(self._flag_ptrs[self.rank]), self.world, self.epoch)
+
     def barrier(self):
         self.epoch += 1
         _lib.call("gq_peer_barrier", ctypes.cast(self._flag_ptrs, ctypes.c_void_p), self.rank, self.world,

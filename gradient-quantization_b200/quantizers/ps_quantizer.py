@@ -1,3 +1,5 @@
+import os
+
 import torch
 
 from .. import _lib
@@ -29,26 +31,39 @@ class PSQuantizer(QuantizerBase):
         if self.plan is not None and self.two_phase:
             self._phase2_plan = None  # built lazily (a 1-user plan for the averaged gradient)
         self.p2p = None
+        self.fused_push = False
         if self.distributed and self.plan is not None:
             self._setup_p2p()
+        if self.distributed and self.two_phase:
+            # the second compression must give the same result on every rank: one shared Philox seed
+            # (rank 0's generator seed), a stream of its own
+            import torch.distributed as dist
+            box = [_lib.PHILOX.share_seed() if self.rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            _lib.PHILOX.share_seed(box[0])
 
     def _setup_p2p(self):
         """Peer-to-peer exchange instead of an NCCL all-gather when every rank can do it
         (args.p2p = False or GQ_P2P=0 turns it off)."""
-        import os
         import torch.distributed as dist
         want = getattr(self.args, "p2p", True) and os.environ.get("GQ_P2P", "1") != "0"
         ok = 1 if (want and self.world <= 8 and self.plan.supports_scattered()) else 0
         p2p = None
+        err = None
         if ok:
             try:
                 from .p2p import PeerRecords
                 p2p = PeerRecords(self.plan.record_bytes, self.rank, self.world, self.device)
             except Exception as e:  # noqa: BLE001
-                print("gq_b200: peer-to-peer exchange unavailable (%s); using NCCL all-gather" % (e,))
+                err = e
                 ok = 0
         flag = torch.tensor([ok], device=self.device)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if want and err is not None and os.environ.get("GQ_P2P_FALLBACK", "0") != "1":
+            # a silent fall-back to NCCL is a 2-3x slower exchange nobody notices: fail loudly unless
+            # the caller opted in (GQ_P2P_FALLBACK=1) or turned peer-to-peer off (GQ_P2P=0 / args.p2p=False)
+            raise _lib.GQError("peer-to-peer exchange could not be set up on rank %d: %r (set GQ_P2P=0 to use "
+                               "the NCCL all-gather, or GQ_P2P_FALLBACK=1 to fall back automatically)" % (self.rank, err))
         if int(flag.item()) == 1:
             self.p2p = p2p
             # "push" (default): store the local record into every peer's block before the barrier
@@ -59,8 +74,29 @@ class PSQuantizer(QuantizerBase):
             if self.p2p_mode not in ("push", "gather", "direct"):
                 raise _lib.GQError("unknown peer-to-peer mode %r" % (self.p2p_mode,))
             self.plan.records = p2p.records          # [2 * U, record_bytes]: row = parity * U + user
+            # push + barrier launches disappear when the encode kernel delivers the record itself
+            self.fused_push = (self.p2p_mode == "push" and os.environ.get("GQ_P2P_FUSED", "1") != "0"
+                               and self.plan.supports_fused_delivery())
         elif p2p is not None:
             p2p.close()
+        if self.rank == 0:
+            print("gq_b200: ps exchange = %s" % self.exchange_name(), flush=True)
+
+    def exchange_name(self):
+        if self.p2p is None:
+            return "NCCL all-gather"
+        if self.p2p_mode == "push":
+            how = "NVLS multicast stores" if self.p2p.mc_base else "peer stores"
+            return ("push fused into the encode kernel, %s, flags instead of a barrier launch" % how
+                    if self.fused_push else "push kernel (%s) + barrier kernel" % how)
+        return self.p2p_mode
+
+    def launches_per_step(self):
+        """My kernel launches in one encode -> exchange -> decode step (bench.py's gpu_launches)."""
+        n = self.plan.launches_per_encode() + self.plan.launches_per_decode(self.world if self.distributed else self.args.num_users)
+        if self.p2p is not None:
+            n += {"push": 0 if self.fused_push else 2, "gather": 2, "direct": 1}[self.p2p_mode]
+        return n
 
     # ------------------------------------------------------------------ record
     def record(self, user, epoch, uniforms=None):
@@ -75,7 +111,7 @@ class PSQuantizer(QuantizerBase):
         if not self.error_feedback:
             flat = plan.locate(grads)
             if flat is not None:          # gradients already form one arena-shaped buffer: read in place
-                plan.encode(slot, src=flat, uniforms=uniforms)
+                self._encode(slot, user, src=flat, uniforms=uniforms)
                 return
         plan.gather(grads)
         if self.error_feedback:
@@ -86,12 +122,19 @@ class PSQuantizer(QuantizerBase):
                       _lib.ptr(plan.arena), _lib.stream())
             for p, v in zip(self.parameters, plan.views()):
                 p.grad.data = v               # the reference mutates param.grad in place
-            plan.encode(slot, uniforms=uniforms)
+            self._encode(slot, user, uniforms=uniforms)
             # error[user] = grad - decompress(compress(grad))   (:36-39)
             dec = plan.decode(first_user=slot, n_users=1, mean=False, out=self._scratch())
             _lib.call("gq_sub", _lib.ptr(plan.arena), _lib.ptr(dec), n, _lib.ptr(err), _lib.stream())
         else:
-            plan.encode(slot, uniforms=uniforms)
+            self._encode(slot, user, uniforms=uniforms)
+
+    def _encode(self, slot, user, src=None, uniforms=None):
+        """Fused encode of `user`'s gradient into row `slot`; with the fused peer-to-peer push the same
+        launch also delivers the record to every rank and announces the step epoch."""
+        if self.fused_push:
+            self.p2p.attach_delivery(self.plan)
+        self.plan.encode(slot, src=src, uniforms=uniforms, rng_user=user)
 
     def _scratch(self):
         if not hasattr(self, "_scratch_buf"):
@@ -115,7 +158,7 @@ class PSQuantizer(QuantizerBase):
         """Pack one user's gradient (the arena, or `src` laid out like it) into its record.
         Returns the row of plan.records that was written."""
         slot = self.p2p.row() if self.p2p is not None else user
-        self.plan.encode(slot, src=src, uniforms=uniforms)
+        self._encode(slot, user, src=src, uniforms=uniforms)
         return slot
 
     def exchange_and_decode(self, out=None):
@@ -125,11 +168,14 @@ class PSQuantizer(QuantizerBase):
         plan = self.plan
         out = plan.arena if out is None else out
         if self.p2p is not None:
-            if self.p2p_mode == "push":
-                self.p2p.push()
-            self.p2p.barrier()
-            if self.p2p_mode == "gather":
-                self.p2p.gather()
+            if self.fused_push:
+                self.p2p.attach_wait()       # the decode kernel waits for every rank's delivery flag itself
+            else:
+                if self.p2p_mode == "push":
+                    self.p2p.push()
+                self.p2p.barrier()
+                if self.p2p_mode == "gather":
+                    self.p2p.gather()
             g = self.decode_exchanged(out)
             self.p2p.advance()
             return g
@@ -176,7 +222,7 @@ class PSQuantizer(QuantizerBase):
                 for p, v in zip(self.parameters, self.plan.views(self._server_err)):
                     p.server_error = v
             _lib.call("gq_axpy", _lib.ptr(g), _lib.ptr(self._server_err), 1.0, n, _lib.ptr(g), _lib.stream())
-        p2.encode(0, src=g, uniforms=uniforms)
+        p2.encode(0, src=g, uniforms=uniforms, shared_rng=True)
         dec = p2.decode(mean=False, out=self._scratch())
         if self.error_feedback:
             _lib.call("gq_sub", _lib.ptr(g), _lib.ptr(dec), n, _lib.ptr(self._server_err), _lib.stream())

@@ -38,7 +38,7 @@ class RingQuantizer(QuantizerBase):
             err = self._ef_buffers(user)
             _lib.call("gq_axpy", _lib.ptr(plan.arena), _lib.ptr(err), float(scale), n,
                       _lib.ptr(plan.arena), _lib.stream())
-        plan.encode(user, uniforms=uniforms)
+        plan.encode(user, uniforms=uniforms, rng_user=user)
         if self.error_feedback:
             if not hasattr(self, "_scratch_buf"):
                 self._scratch_buf = torch.empty_like(plan.arena)
@@ -46,6 +46,37 @@ class RingQuantizer(QuantizerBase):
             _lib.call("gq_sub", _lib.ptr(plan.arena), _lib.ptr(dec), n, _lib.ptr(err), _lib.stream())
         if self.distributed:
             xch.ring_send_next(plan.records, user, self.world)
+
+    def step_buffers(self, src, out):
+        """One ring step on raw arena-shaped device buffers (bench.py): this rank's hop -- receive the
+        previous hop's record, add its decode to the local gradient IN PLACE (ring_quantizer.py:31-32
+        mutates param.grad), encode the sum, send it on -- then the broadcast of the last hop and the
+        final decode into `out`.  Single process: all users' hops one after the other on `src`."""
+        plan = self.plan
+        users = [self.rank] if self.distributed else range(self.args.num_users)
+        for user in users:
+            if user != 0:
+                if self.distributed:
+                    xch.ring_receive_previous(plan.records, user)
+                plan.decode(first_user=user - 1, n_users=1, mean=False, accumulate=True, out=src)
+            plan.encode(user, src=src)
+            if self.distributed:
+                xch.ring_send_next(plan.records, user, self.world)
+        last = self.args.num_users - 1
+        if self.distributed:
+            xch.ring_broadcast_last(plan.records, self.world)
+        return plan.decode(first_user=last, n_users=1, mean=False, out=out)
+
+    def launches_per_step(self):
+        """My kernel launches per rank and step: (decode-accumulate +) encode + final decode."""
+        n = self.plan.launches_per_encode() + self.plan.launches_per_decode(1)
+        if self.distributed:
+            return n + (self.plan.launches_per_decode(1) if self.rank > 0 else 0)
+        u = self.args.num_users
+        return u * self.plan.launches_per_encode() + u * self.plan.launches_per_decode(1)
+
+    def exchange_name(self):
+        return "NCCL send/recv chain + broadcast" if self.distributed else "none"
 
     def _record_per_parameter(self, user, scale):
         for i, param in enumerate(self.parameters):

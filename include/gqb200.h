@@ -236,6 +236,14 @@ int gq_hsq_tc_debug(const float *grad, int64_t n_chunks, const float *codebook, 
                     float *u_out, const int64_t *seg_start, int n_seg, float *dbg_scores,
                     int dbg_tiles, gq_stream_t stream);
 
+/* Multi-tensor gather: copy n_tensors fp32 tensors (src_ptrs: HOST array of device pointers,
+ * sizes in elements) to dst + dst_offsets[t] (elements) -- how the per-parameter gradients of
+ * main.py:229-230 (param.grad after loss.backward()) reach the codec arena that
+ * PSQuantizer.record / RingQuantizer.record (quantizers/ps_quantizer.py:33-44) encode from.
+ * One launch per 128 tensors; the pointer table travels as a kernel parameter. */
+int gq_gather_f32(const void *const *src_ptrs, const int64_t *dst_offsets, const int64_t *sizes,
+                  int n_tensors, float *dst, gq_stream_t stream);
+
 /* Diagnostic hook for the second-generation tcgen05 kernel: search only, and CTA 0 time-stamps
  * the pipeline events of its first 128 tiles into trace (device int64 [9 * 128], clock64 values;
  * event list in hsq_tc2.cu).  How tests/tc2_trace.py measures where a tile's time goes. */
@@ -273,6 +281,19 @@ int gq_peer_push(const void *src, void *const *dst_ptrs, size_t bytes, int n_dst
  * mc_dst = multicast address of the destination row (identical offset in every rank's buffer).
  * One multimem.st per 16 bytes is replicated by the switch to every rank (the sender included). */
 int gq_peer_push_multicast(const void *src, void *mc_dst, size_t bytes, gq_stream_t stream);
+
+/* Exchange fused into the codec kernels (default for HSQ d=16 K=256 on one NVSwitch node).
+ * Sending side: the next gq_hsq_encode on this host thread also stores every finished section of
+ * the record at (local address + delta[i]), i < n_remote -- the same record row in the peers'
+ * receive blocks -- or once through an NVLS multicast mapping (multicast = 1, n_remote = 1),
+ * mirrors the identity section [ident, ident + ident_bytes), and when the whole record is out stores
+ * `epoch` (system-scope release) into flag_ptrs[0..n_flags): this rank's word in every rank's flag
+ * array.  Receiving side: the next HSQ decode first waits until n_ranks words of local_flags have
+ * reached `epoch`.  Together they replace gq_peer_push* + gq_peer_barrier (two launches per step)
+ * of the exchange step of PSQuantizer (quantizers/ps_quantizer.py:44-48). */
+int gq_attach_remote_record(int n_remote, int multicast, const int64_t *delta, const void *ident,
+                            int64_t ident_bytes, void *const *flag_ptrs, int n_flags, uint32_t epoch);
+int gq_attach_peer_wait(const void *local_flags, int n_ranks, uint32_t epoch);
 
 /* ------------------------------------------------------------------------- */
 /* Elementwise helpers the quantizers need around the codecs.

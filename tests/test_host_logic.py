@@ -123,16 +123,18 @@ def test_plan_locates_arena_shaped_gradients_and_counts_launches():
     moved[1] = torch.zeros_like(views[1])                        # one tensor lives elsewhere: copy path
     assert plan.locate(moved) is None
     assert plan.locate(views[:-1]) is None
-    # ResNet-50 / HSQ d=16 K=256 n=6: search (resets the keys, carries the identity copy) + quantize,
-    # and one decode kernel that also reduces the identity tensors
+    # ResNet-50 / HSQ d=16 K=256 n=6: ONE encode launch (key reset, identity copy, search, fused norm
+    # quantization) and one decode kernel that also reduces the identity tensors
     big = FusedPlan(gq_b200.NearestNeighborCompressor, resnet50_shapes(), a, torch.device("cpu"), 2)
-    assert big.launches_per_encode() == 2 and big.launches_per_decode(2) == 1
+    assert big.launches_per_encode() == 1 and big.launches_per_decode(2) == 1
+    assert big.supports_fused_delivery()
     from gq_b200 import _lib
     exact = FusedPlan(gq_b200.NearestNeighborCompressor, resnet50_shapes(), make_args(hsq_algo=_lib.ALGO_EXACT),
                       torch.device("cpu"), 2)
     assert exact.launches_per_encode() == 3                      # init + search + quantize
     d8 = FusedPlan(gq_b200.NearestNeighborCompressor, resnet50_shapes(), make_args(c_dim=8), torch.device("cpu"), 2)
     assert d8.launches_per_encode() == 3 and d8.launches_per_decode(2) == 2   # identity reduce on its own
+    assert not d8.supports_fused_delivery() and not exact.supports_fused_delivery()
 
 
 def test_peer_records_row_and_address_arithmetic():
