@@ -207,14 +207,18 @@ class PSQuantizer(QuantizerBase):
             g = self._second_phase(g, uniforms)
         self._set_grads_from(g)
 
+    def phase2_plan(self):
+        """The 1-user plan that compresses the averaged gradient once more (--two-phase); built lazily."""
+        from .fused import FusedPlan
+        if self._phase2_plan is None:
+            self._phase2_plan = FusedPlan(self.plan.Compressor, self.plan.shapes, self.args, self.device, 1)
+        return self._phase2_plan
+
     def _second_phase(self, g, uniforms):
         """Compress the averaged gradient once more (ps_quantizer.py:52-61).  Every rank
         holds the same average; with identical uniforms (or the shared Philox state)
         every rank computes the same result."""
-        from .fused import FusedPlan
-        if self._phase2_plan is None:
-            self._phase2_plan = FusedPlan(self.plan.Compressor, self.plan.shapes, self.args, self.device, 1)
-        p2 = self._phase2_plan
+        p2 = self.phase2_plan()
         n = g.numel()
         if self.error_feedback:
             if not hasattr(self, "_server_err"):

@@ -305,7 +305,10 @@ class Identity:
 
 
 class PVC:
-    """ProbabilisticVectorCompressor, intended semantics (a7). PARITY UNPINNED."""
+    """ProbabilisticVectorCompressor (a7).  Pinned against the reference's own arithmetic for every
+    line that executes (tests/golden/make_golden.py:pvc_case); the one line that does not --
+    `argmin` on a bool tensor, :57-58 -- is read as "first index whose cumulative probability
+    reaches r - 1e-5" (what argmin + 1 gave on the ByteTensors of the PyTorch it was written for)."""
 
     def __init__(self, size, shape, cb, n_bit, random=True):
         self.size, self.shape = size, tuple(shape)
@@ -363,9 +366,10 @@ def ps_scale(epoch, scale="exp"):
     return (2 / (math.exp(-epoch) + 1) - 1) if scale == "exp" else float(scale)
 
 
-def ps_step(codecs, user_grads, stream=None, ef_errors=None, scale=0.0):
-    """ps_quantizer.py:27-65 without two_phase: user_grads[u][i] -> averaged grads[i].
-    ef_errors[u][i] (updated in place) enables error feedback."""
+def ps_step(codecs, user_grads, stream=None, ef_errors=None, scale=0.0, two_phase=False, server_errors=None):
+    """ps_quantizer.py:27-65: user_grads[u][i] -> the gradients apply() leaves in param.grad.
+    ef_errors[u][i] (updated in place) enables error feedback (:34-39); two_phase compresses the
+    average once more (:52-61), with server_errors[i] (updated in place) when error feedback is on."""
     U = len(user_grads)
     out = []
     dec = [[None] * len(codecs) for _ in range(U)]
@@ -378,14 +382,24 @@ def ps_step(codecs, user_grads, stream=None, ef_errors=None, scale=0.0):
             if ef_errors is not None:
                 ef_errors[u][i] = g - d
             dec[u][i] = d
-    for i in range(len(codecs)):
+    for i, c in enumerate(codecs):
         stack = np.stack([dec[u][i].reshape(-1) for u in range(U)])
-        out.append(ps_mean(stack).reshape(dec[0][i].shape))
+        g = ps_mean(stack).reshape(dec[0][i].shape)
+        if two_phase:
+            if server_errors is not None:
+                g = g + server_errors[i]
+                d = c.decompress(c.compress(g, stream))
+                server_errors[i] = g - d
+                g = d
+            else:
+                g = c.decompress(c.compress(g, stream))
+        out.append(g)
     return out
 
 
-def ring_step(codecs, user_grads, stream=None):
-    """ring_quantizer.py:25-49 (no error feedback): the lossy running SUM."""
+def ring_step(codecs, user_grads, stream=None, ef_errors=None, scale=0.0):
+    """ring_quantizer.py:25-49: the lossy running SUM; ef_errors[u][i] (updated in place)
+    enables error feedback (:33-38)."""
     U = len(user_grads)
     prev = [None] * len(codecs)
     for u in range(U):
@@ -393,5 +407,10 @@ def ring_step(codecs, user_grads, stream=None):
             g = np.asarray(user_grads[u][i], dtype=np.float32)
             if u != 0:
                 g = g + prev[i]
-            prev[i] = c.decompress(c.compress(g, stream))
+            if ef_errors is not None:
+                g = g + np.float32(scale) * ef_errors[u][i]
+            d = c.decompress(c.compress(g, stream))
+            if ef_errors is not None:
+                ef_errors[u][i] = g - d
+            prev[i] = d
     return prev

@@ -191,6 +191,43 @@ def test_pvc_and_residual_vs_oracle(d, k_bit):
     assert np.array_equal(res.decompress(sigs).cpu().numpy(), orc.decompress(osigs))
 
 
+@pytest.mark.parametrize("name", golden_names("pvc_") + golden_names("residual_"))
+def test_pvc_and_residual_vs_reference_golden(name):
+    """The reference's own ProbabilisticVectorCompressor / ResidualCompressor outputs
+    (tests/golden/make_golden.py:pvc_case), codes / levels / lb-ub / decoded bit for bit."""
+    g = golden(name)
+    n, d, k_bit, n_bit = int(g["n_chunks"]), int(g["d"]), int(g["k_bit"]), int(g["n_bit"])
+    size = n * d
+    x = gen_input(int(g["seed"]), size)
+    a = make_args(c_dim=d, k_bit=k_bit, n_bit=n_bit)
+    draws = g["draws"]
+    cb = torch.from_numpy(g["codewords"]).to(DEV)
+    dag = torch.from_numpy(g["dagger"]).to(DEV)
+
+    def check(sig, pre):
+        assert np.array_equal(sig[1].cpu().numpy().astype(np.int32), g[pre + "codes"])
+        if n_bit != 32:
+            assert np.float32(sig[0][0].item()) == g[pre + "lb"] and np.float32(sig[0][1].item()) == g[pre + "ub"]
+            assert np.array_equal(sig[0][2].cpu().numpy(), g[pre + "l"])
+        else:
+            assert np.array_equal(sig[0].cpu().numpy(), g[pre + "u"])
+
+    if int(g["residual"]):
+        c = gq_b200.ResidualCompressor(size, torch.Size((n, d)), a)
+        assert np.array_equal(c.compressors[0].codewords.cpu().numpy(), g["codewords"])
+        c.compressors[1].codewords, c.compressors[1].c_dagger = cb, dag
+        sig = c.compress(_t(x).view(n, d), uniforms=[dict(uniforms=draws[:n]),
+                                                      dict(uniforms=draws[n:2 * n], norm_uniforms=draws[2 * n:])])
+        check(sig[0], "s1_")
+        check(sig[1], "s2_")
+    else:
+        c = gq_b200.ProbabilisticVectorCompressor(size, torch.Size((n, d)), a)
+        c.codewords, c.c_dagger = cb, dag       # K == d: the reference drew a random orthogonal basis
+        sig = c.compress(_t(x).view(n, d), uniforms=draws[:n], norm_uniforms=draws[n:] if n_bit != 32 else None)
+        check(sig, "")
+    assert np.array_equal(c.decompress(sig).cpu().numpy().reshape(-1), g["decoded"])
+
+
 def test_pvc_is_unbiased():
     d, size = 16, 16 * 64
     a = make_args(c_dim=d, k_bit=8, n_bit=32)

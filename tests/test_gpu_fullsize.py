@@ -1,7 +1,8 @@
 """GPU, BASELINE.json's full sizes (ResNet-50 gradient: 23 520 842 elements, 76 compressed tensors):
-size-independent properties instead of a full CPU oracle pass -- two independent CUDA
-implementations agree everywhere, the oracle agrees on a random sample of chunks, and the
-codec's algebraic invariants hold."""
+the CPU oracle over the WHOLE gradient (every chunk's code, u, level, every tensor's lb/ub; the C
+port does a user-pass in about a second), the 8-user ps record/apply flow and the QSGD / TernGrad /
+sign / top-k codecs at the same size against the oracle, two independent CUDA implementations
+against each other, and the codec's algebraic invariants."""
 import numpy as np
 import pytest
 import torch
@@ -48,20 +49,121 @@ def test_tcgen05_and_exact_kernels_agree_on_every_chunk(plans):
     assert torch.equal(pl["tc"].u_scratch[:n], pl["exact"].u_scratch[:n])
 
 
-def test_oracle_agrees_on_a_random_sample_of_chunks(plans):
+def test_oracle_agrees_on_every_chunk_of_the_whole_gradient(plans):
+    """codes, u, l and lb/ub of all 1 468 652 chunks / 76 tensors against the CPU oracle."""
     pl, g = plans
     p = pl["tc"]
     grp = p.groups[0]
-    p.encode(1, src=g)
+    n = grp.n_chunks
+    uni = torch.rand(n, device=DEV, generator=torch.Generator(device=DEV).manual_seed(11))
+    p.random = 1
+    p.encode(1, src=g, uniforms={id(grp): uni})
     torch.cuda.synchronize()
-    rs = np.random.RandomState(0)
-    idx = np.unique(np.concatenate([rs.randint(0, grp.n_chunks, 60000), np.arange(0, 4096),
-                                    np.arange(grp.n_chunks - 4096, grp.n_chunks)]))
-    chunks = g[grp.arena_off:grp.arena_off + grp.n].view(-1, 16)[torch.from_numpy(idx).to(DEV)].cpu().numpy()
+    chunks = g[grp.arena_off:grp.arena_off + grp.n].view(-1, 16).cpu().numpy()
     oc, ou = O.hsq_search(chunks, codebook(16, 256))
-    codes = p.records[1][grp.codes_off:grp.codes_off + grp.n_chunks].cpu().numpy()[idx]
-    assert np.array_equal(codes.astype(np.int32), oc)
-    assert np.array_equal(p.u_scratch[:grp.n_chunks].cpu().numpy()[idx], ou)
+    rec = p.records[1]
+    assert np.array_equal(rec[grp.codes_off:grp.codes_off + n].cpu().numpy().astype(np.int32), oc)
+    assert np.array_equal(p.u_scratch[:n].cpu().numpy(), ou)
+    l = rec[grp.l_off:grp.l_off + n].cpu().numpy()
+    lbub = rec[grp.lbub_off:grp.lbub_off + 8 * grp.n_seg].view(torch.float32).view(-1, 2).cpu().numpy()
+    r = uni.cpu().numpy()
+    starts = grp.seg_start_host
+    for sg in range(grp.n_seg):
+        a, b = starts[sg], starts[sg + 1]
+        lb, ub, ol, used = O.psc_compress(ou[a:b], 6, True, r[a:b])
+        assert lbub[sg, 0] == lb and lbub[sg, 1] == ub, sg
+        assert np.array_equal(l[a:b].astype(np.int32), ol), sg
+
+
+def test_eight_user_ps_step_equals_the_oracle_at_full_size():
+    """PSQuantizer.record x 8 + apply() on the ResNet-50 shapes against oracle.ps_step
+    (ps_quantizer.py:27-65), same external uniform stream; decode over U = 8 records at full size."""
+    shapes = resnet50_shapes()
+    sizes = [int(np.prod(s)) for s in shapes]
+    U = 8
+    a = make_args(num_users=U)
+    params = [torch.nn.Parameter(torch.zeros(s, device=DEV)) for s in shapes]
+    q = gq_b200.Quantizer(gq_b200.NearestNeighborCompressor, params, a)
+    plan = q.plan
+    gen = torch.Generator(device=DEV)
+    gen.manual_seed(21)
+    per_user = sum(n // 16 for n in sizes if n > 1000)
+    rs = np.random.RandomState(5)
+    draws = rs.random_sample(per_user * U).astype(np.float32)
+    grads = []
+    for u in range(U):
+        flat = torch.randn(plan.arena_elems, device=DEV, generator=gen) * (0.01 * (u + 1))
+        views = plan.views(flat)
+        grads.append([v.cpu().numpy() for v in views])
+        for p, v in zip(params, views):
+            p.grad = v.clone()              # ordinary per-parameter tensors: the gather kernel runs
+        parts, used = plan.split_uniform_stream(draws[u * per_user:(u + 1) * per_user])
+        assert used == per_user
+        q.record(u, epoch=1, uniforms=parts)
+    q.apply()
+    torch.cuda.synchronize()
+    cb = codebook(16, 256)
+    codecs = [O.HSQ(n, s, cb, 6, True) if n > 1000 else O.Identity() for n, s in zip(sizes, shapes)]
+    ref = O.ps_step(codecs, grads, O.UniformStream(draws))
+    for i, (p, r_) in enumerate(zip(params, ref)):
+        got = p.grad.data.cpu().numpy()
+        r_ = r_.reshape(got.shape)
+        if got.size >= 256:
+            assert np.array_equal(got, r_), i
+        else:
+            assert np.abs(got - r_).max() <= 1e-6 * max(np.abs(r_).max(), 1e-30), i
+
+
+@pytest.mark.parametrize("quant,kw", [("qsgd", dict(c_dim=128, n_bit=2)), ("terngrad", dict(c_dim=0, n_bit=1)),
+                                      ("sign", {}), ("topk", dict(cr=100))])
+def test_elementwise_codecs_equal_the_oracle_at_full_size(quant, kw):
+    """QSGD d=128 2-bit (first conv: dim 192), TernGrad, sign and top-k 1 % on the ResNet-50 shapes,
+    two users through PSQuantizer.record/apply against the oracle (BASELINE configs 3 and 5)."""
+    shapes = resnet50_shapes()
+    sizes = [int(np.prod(s)) for s in shapes]
+    U = 2
+    a = make_args(num_users=U, **kw)
+    Comp = {"qsgd": gq_b200.QSGDCompressor, "terngrad": gq_b200.QSGDCompressor, "sign": gq_b200.SignSGDCompressor,
+            "topk": gq_b200.TopKSparsificationCompressor}[quant]
+    params = [torch.nn.Parameter(torch.zeros(s, device=DEV)) for s in shapes]
+    q = gq_b200.Quantizer(Comp, params, a)
+    plan = q.plan
+    gen = torch.Generator(device=DEV)
+    gen.manual_seed(31)
+    per_user = sum(n for n in sizes if n > 1000) if quant in ("qsgd", "terngrad") else 0
+    draws = np.random.RandomState(6).random_sample(per_user * U).astype(np.float32)
+    grads = []
+    for u in range(U):
+        flat = torch.randn(plan.arena_elems, device=DEV, generator=gen) * 0.01
+        if quant == "qsgd":
+            flat[1000:5000] = 0.0          # some all-zero chunks (the 0/0 -> INT32_MIN edge)
+        views = plan.views(flat)
+        grads.append([v.cpu().numpy() for v in views])
+        for p, v in zip(params, views):
+            p.grad = v.clone()
+        parts, used = plan.split_uniform_stream(draws[u * per_user:(u + 1) * per_user])
+        assert used == per_user
+        q.record(u, epoch=1, uniforms=parts)
+    q.apply()
+    torch.cuda.synchronize()
+    codecs = []
+    for n, s in zip(sizes, shapes):
+        if n <= 1000:
+            codecs.append(O.Identity())
+        elif quant in ("qsgd", "terngrad"):
+            codecs.append(O.QSGD(n, s, a.c_dim, a.n_bit, True))
+        elif quant == "sign":
+            codecs.append(O.Sign(n, s))
+        else:
+            codecs.append(O.TopK(n, s, a.cr))
+    ref = O.ps_step(codecs, grads, O.UniformStream(draws))
+    for i, (p, r_) in enumerate(zip(params, ref)):
+        got = p.grad.data.cpu().numpy()
+        r_ = r_.reshape(got.shape)
+        if got.size >= 256:
+            assert np.array_equal(got, r_), (quant, i)
+        else:
+            assert np.abs(got - r_).max() <= 1e-6 * max(np.abs(r_).max(), 1e-30), (quant, i)
 
 
 def test_levels_bounds_and_roundtrip_error(plans):

@@ -19,7 +19,8 @@ def _run(g, fused):
     U, seed, iters = int(g["U"]), int(g["seed"]), int(g["iters"])
     shapes = [tuple(int(x) for x in g["shape%d" % i]) for i in range(int(g["n_tensors"]))]
     sizes = [int(np.prod(s)) for s in shapes]
-    a = make_args(mode=str(g["mode"]), num_users=U, ef=bool(int(g["ef"])), c_dim=int(g["c_dim"]),
+    two_phase = bool(int(g["two_phase"])) if "two_phase" in g else False
+    a = make_args(mode=str(g["mode"]), num_users=U, ef=bool(int(g["ef"])), two_phase=two_phase, c_dim=int(g["c_dim"]),
                   k_bit=int(g["k_bit"]), n_bit=int(g["n_bit"]), cr=int(g["cr"]), fused=fused)
     params = [torch.nn.Parameter(torch.zeros(s, device=DEV)) for s in shapes]
     q = gq_b200.Quantizer(getattr(gq_b200, COMP[str(g["quant"])]), params, a)
@@ -33,7 +34,12 @@ def _run(g, fused):
             parts, used = q.plan.split_uniform_stream(stream[pos:])
             pos += used
             q.record(u, epoch=int(g["epoch"]), uniforms=parts)
-        q.apply()
+        if two_phase:   # the second compression draws from the same stream, after every user's record
+            parts, used = q.phase2_plan().split_uniform_stream(stream[pos:])
+            pos += used
+            q.apply(uniforms=parts)
+        else:
+            q.apply()
         for i, p in enumerate(params):
             ref = g["grad_it%d_t%d" % (it, i)]
             got = p.grad.data.cpu().numpy().reshape(-1)

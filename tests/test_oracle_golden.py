@@ -78,13 +78,15 @@ def _quantizer_replay(g):
             codecs.append(O.TopK(n, s, int(g["cr"])))
     stream = O.UniformStream(torch_uniform_stream(seed, int(g["n_draws"])))
     errs = [[np.zeros(s, np.float32) for s in shapes] for _ in range(U)] if int(g["ef"]) else None
+    two_phase = bool(int(g["two_phase"])) if "two_phase" in g else False
+    serrs = [np.zeros(s, np.float32) for s in shapes] if (two_phase and int(g["ef"])) else None
     for it in range(iters):
         grads = [[gen_input(seed * 1000 + it * 100 + u * 10 + i, n).reshape(s)
                   for i, (n, s) in enumerate(zip(sizes, shapes))] for u in range(U)]
         if str(g["mode"]) == "ps":
-            out = O.ps_step(codecs, grads, stream, errs, O.ps_scale(int(g["epoch"])))
+            out = O.ps_step(codecs, grads, stream, errs, O.ps_scale(int(g["epoch"])), two_phase, serrs)
         else:
-            out = O.ring_step(codecs, grads, stream)
+            out = O.ring_step(codecs, grads, stream, errs, O.ps_scale(int(g["epoch"])))
         for i in range(len(shapes)):
             ref = g["grad_it%d_t%d" % (it, i)]
             got = out[i].reshape(-1)
@@ -100,6 +102,39 @@ def _quantizer_replay(g):
 @pytest.mark.parametrize("name", golden_names("ps_") + golden_names("ring_"))
 def test_quantizer_fixture(name):
     _quantizer_replay(golden(name))
+
+
+def _check_sig(sig, g, pre, n_bit):
+    assert np.array_equal(sig[1], g[pre + "codes"])
+    if n_bit != 32:
+        assert sig[0][0] == g[pre + "lb"] and sig[0][1] == g[pre + "ub"]
+        assert np.array_equal(sig[0][2], g[pre + "l"])
+    else:
+        assert np.array_equal(sig[0], g[pre + "u"])
+
+
+@pytest.mark.parametrize("name", golden_names("pvc_") + golden_names("residual_"))
+def test_pvc_and_residual_fixture(name):
+    """ProbabilisticVectorCompressor / ResidualCompressor outputs of the reference's own code
+    (make_golden.py:_runnable_pvc documents the one line that had to be read, not run)."""
+    g = golden(name)
+    n, d, n_bit = int(g["n_chunks"]), int(g["d"]), int(g["n_bit"])
+    x = gen_input(int(g["seed"]), n * d)
+    cb = g["codewords"]
+    assert np.array_equal(np.linalg.pinv(cb.T).astype(np.float32), g["dagger"])
+    assert np.array_equal(g["draws"], torch_uniform_stream(int(g["seed"]), g["draws"].size))
+    stream = O.UniformStream(g["draws"])
+    if int(g["residual"]):
+        c = O.Residual(n * d, (n, d), cb, n_bit, True)
+        sig = c.compress(x, stream)
+        _check_sig(sig[0], g, "s1_", n_bit)
+        _check_sig(sig[1], g, "s2_", n_bit)
+    else:
+        c = O.PVC(n * d, (n, d), cb, n_bit, True)
+        sig = c.compress(x, stream)
+        _check_sig(sig, g, "", n_bit)
+    assert stream.pos == g["draws"].size
+    assert np.array_equal(c.decompress(sig).reshape(-1), g["decoded"])
 
 
 def test_psc_levels_cover_2n_plus_1():
