@@ -175,7 +175,7 @@ __device__ __forceinline__ void issue_tile_mma(uint32_t a_addr, uint32_t b_addr,
 // clock64(): 0 TMA issued, 1 MMA issued, 2 accumulators seen by the epilogue warp, 3 TMEM released
 // (first pass done), 4 smem stage released, 5 candidate mask done, 6 rescoring done, 7 tile done,
 // 8 rescoring iterations of the warp (count, not a time); taken by quadrant 0 / lane 0 of each group.
-template <int G, bool PAIR, bool FMASK, bool F2, bool TRACE = false>
+template <int G, bool PAIR, bool FMASK, bool F2, bool R2 = false, bool TRACE = false>
 __global__ void __launch_bounds__(128 + 128 * G, 1)
 hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_constant__ Enc2 P)
 {
@@ -522,13 +522,8 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
 #pragma unroll
                 for (int j = 0; j < kD; ++j) vv[j] = pack2(v[j], v[j]);
             }
-            uint32_t cur = clo, nxt = chi;
-            int gbase = 0;
-            if (cur == 0u) { cur = nxt; nxt = 0u; gbase = 32; }
-            while (cur != 0u) {
-                const int g = gbase + __ffs((int)cur) - 1;
-                cur &= cur - 1u;
-                float p[kGroup];
+            // exact scores of the four codewords of group g (ascending-j chain, as hsq_exact.cu)
+            auto score_group = [&](int g, float (&p)[kGroup]) {
                 if constexpr (F2) {
                     const uint32_t slot = pbase + (uint32_t)g * 256u;   // pair 2g at slot, pair 2g + 1 at slot + 128
                     unsigned long long a01, a23;
@@ -566,6 +561,10 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
                         p[i] = acc;
                     }
                 }
+            };
+            // group maximum first (3 FMNMX), one compare against the running best, and only a winning
+            // group pays for locating its first maximal codeword (first index wins ties: groups ascend)
+            auto take_group = [&](int g, const float (&p)[kGroup]) {
                 const float gmax = fmaxf(fmaxf(fabsf(p[0]), fabsf(p[1])), fmaxf(fabsf(p[2]), fabsf(p[3])));
                 const int gb = __float_as_int(gmax);
                 const float psum = (p[0] + p[1]) + (p[2] + p[3]);   // NaN (or inf - inf) takes the slow path
@@ -576,7 +575,35 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
                         if (ab > best_bits) { best_bits = ab; best_k = g * kGroup + i; best_u = p[i]; }
                     }
                 }
+            };
+            uint32_t cur = clo, nxt = chi;
+            int gbase = 0;
+            if (cur == 0u) { cur = nxt; nxt = 0u; gbase = 32; }
+            while (cur != 0u) {
+                const int g0 = gbase + __ffs((int)cur) - 1;
+                cur &= cur - 1u;
                 if (cur == 0u) { cur = nxt; nxt = 0u; gbase = 32; }
+                if constexpr (R2) {
+                    // two candidate groups per pass: their FMA chains interleave (twice the ILP of a
+                    // latency-bound loop).  About a fifth of the rows have a second candidate, so nearly
+                    // every warp ran a second pass anyway; a row without one rescoring its group twice is
+                    // harmless (the repeat never beats the running best).
+                    int g1 = g0;
+                    if (cur != 0u) {
+                        g1 = gbase + __ffs((int)cur) - 1;
+                        cur &= cur - 1u;
+                        if (cur == 0u) { cur = nxt; nxt = 0u; gbase = 32; }
+                    }
+                    float p0[kGroup], p1[kGroup];
+                    score_group(g0, p0);
+                    score_group(g1, p1);
+                    take_group(g0, p0);
+                    take_group(g1, p1);
+                } else {
+                    float p0[kGroup];
+                    score_group(g0, p0);
+                    take_group(g0, p0);
+                }
                 if (TRACE) ++n_iter;
             }
             __syncwarp();
@@ -595,6 +622,7 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
                 if (!keys_ready) {   // CTA 0 has reset the keys; bounded wait, then trap
                     unsigned long long seen;
                     uint32_t spins = 0;
+#pragma unroll 1
                     do {
                         asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(P.flag) : "memory");
                         if (seen == P.id) break;
@@ -824,28 +852,29 @@ static int make_map(CUtensorMap *map, const float *base, int64_t rows)
 
 struct Variant {
     int groups;
-    bool pair, fmask, f2;
+    bool pair, fmask, f2, r2;
 };
 
-// GQ_TC2 = comma-separated switches, read at every launch (A/B runs): g3 | g4, pair, nopair, fmask,
-// nofmask, f2, nof2
+// GQ_TC2 = comma-separated switches, read at every launch (A/B runs): g3 | g4, pair | nopair,
+// fmask | nofmask, f2 | nof2, r2 | r1.  Only the combinations instantiated below exist.
 static Variant pick_variant()
 {
-    Variant v = {3, true, true, true};
+    Variant v = {3, true, true, true, true};
     if (const char *e = getenv("GQ_TC2")) {
         if (strstr(e, "g4")) v.groups = 4;
         if (strstr(e, "g3")) v.groups = 3;
         if (strstr(e, "nopair")) v.pair = false; else if (strstr(e, "pair")) v.pair = true;
         if (strstr(e, "nofmask")) v.fmask = false; else if (strstr(e, "fmask")) v.fmask = true;
         if (strstr(e, "nof2")) v.f2 = false; else if (strstr(e, "f2")) v.f2 = true;
+        if (strstr(e, "r1")) v.r2 = false; else if (strstr(e, "r2")) v.r2 = true;
     }
     return v;
 }
 
-template <int G, bool PAIR, bool FMASK, bool F2>
+template <int G, bool PAIR, bool FMASK, bool F2, bool R2>
 static int launch_one(const CUtensorMap &mg, const Enc2 &P, int grid, cudaStream_t st)
 {
-    auto kern = hsq_encode_tc2_kernel<G, PAIR, FMASK, F2>;
+    auto kern = hsq_encode_tc2_kernel<G, PAIR, FMASK, F2, R2, false>;
     static bool attr_set = false;   // per instantiation
     if (!attr_set) {
         GQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Layout<G>::kSmemBytes));
@@ -855,19 +884,24 @@ static int launch_one(const CUtensorMap &mg, const Enc2 &P, int grid, cudaStream
     return GQ_OK;
 }
 
-template <int G>
-static int launch_g(const Variant &v, const CUtensorMap &mg, const Enc2 &P, int grid, cudaStream_t st)
+static int launch_variant(const Variant &v, const CUtensorMap &mg, const Enc2 &P, int grid, cudaStream_t st)
 {
-    const int sel = (v.pair ? 4 : 0) | (v.fmask ? 2 : 0) | (v.f2 ? 1 : 0);
+    const int sel = (v.groups == 4 ? 16 : 0) | (v.pair ? 8 : 0) | (v.fmask ? 4 : 0) | (v.f2 ? 2 : 0) | (v.r2 ? 1 : 0);
     switch (sel) {
-    case 0: return launch_one<G, false, false, false>(mg, P, grid, st);
-    case 1: return launch_one<G, false, false, true>(mg, P, grid, st);
-    case 2: return launch_one<G, false, true, false>(mg, P, grid, st);
-    case 3: return launch_one<G, false, true, true>(mg, P, grid, st);
-    case 4: return launch_one<G, true, false, false>(mg, P, grid, st);
-    case 5: return launch_one<G, true, false, true>(mg, P, grid, st);
-    case 6: return launch_one<G, true, true, false>(mg, P, grid, st);
-    default: return launch_one<G, true, true, true>(mg, P, grid, st);
+    case 0: return launch_one<3, false, false, false, false>(mg, P, grid, st);   // structural changes only
+    case 8: return launch_one<3, true, false, false, false>(mg, P, grid, st);
+    case 12: return launch_one<3, true, true, false, false>(mg, P, grid, st);
+    case 13: return launch_one<3, true, true, false, true>(mg, P, grid, st);
+    case 14: return launch_one<3, true, true, true, false>(mg, P, grid, st);
+    case 15: return launch_one<3, true, true, true, true>(mg, P, grid, st);
+    case 9: return launch_one<3, true, false, false, true>(mg, P, grid, st);
+    case 16 + 14: return launch_one<4, true, true, true, false>(mg, P, grid, st);
+    case 16 + 15: return launch_one<4, true, true, true, true>(mg, P, grid, st);
+    case 16 + 13: return launch_one<4, true, true, false, true>(mg, P, grid, st);
+    case 16 + 12: return launch_one<4, true, true, false, false>(mg, P, grid, st);
+    default:
+        set_error("GQ_TC2: this combination of switches is not built");
+        return GQ_ERR_UNSUPPORTED;
     }
 }
 
@@ -902,8 +936,9 @@ int hsq_search_tc2_trace(const float *grad, int64_t n_chunks, const float *codeb
         GQ_CUDA(launch_pdl(kern, dim3(grid), dim3(threads), smem, st, mg, P));
         return GQ_OK;
     };
-    if (v.pair) e = launch(hsq_encode_tc2_kernel<3, true, true, true, true>, 512, Layout<3>::kSmemBytes);
-    else e = launch(hsq_encode_tc2_kernel<3, false, false, false, true>, 512, Layout<3>::kSmemBytes);
+    if (v.groups == 4) e = launch(hsq_encode_tc2_kernel<4, true, true, true, true, true>, 640, Layout<4>::kSmemBytes);
+    else if (v.r2) e = launch(hsq_encode_tc2_kernel<3, true, true, true, true, true>, 512, Layout<3>::kSmemBytes);
+    else e = launch(hsq_encode_tc2_kernel<3, true, true, true, false, true>, 512, Layout<3>::kSmemBytes);
     if (e) return e;
     GQ_LAUNCH_CHECK("hsq_search_tc2_trace");
     return GQ_OK;
@@ -975,7 +1010,7 @@ int hsq_encode_tc2(const float *grad, int64_t n_chunks, const float *codebook, v
     }
     const int grid = n_tiles < sms ? n_tiles : sms;
     const Variant v = pick_variant();
-    e = (v.groups == 4) ? launch_g<4>(v, mg, P, grid, st) : launch_g<3>(v, mg, P, grid, st);
+    e = launch_variant(v, mg, P, grid, st);
     if (e) return e;
     GQ_LAUNCH_CHECK("hsq_encode_tc2");
     return GQ_OK;
