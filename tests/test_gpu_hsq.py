@@ -235,3 +235,29 @@ def test_errors_are_loud():
                   None, 1, None, 1, None, None, None, 0, 0, _lib.stream())
     with pytest.raises(_lib.GQError):
         gq_b200.NearestNeighborCompressor(4096, (64, 64), make_args()).compress(torch.zeros(4096))
+
+
+def test_codebook_generator_on_gpu_and_k65536_search():
+    """The generator's HSQ objective runs this package's search kernel; a synthesised K = 2^16
+    codebook (BASELINE config 4: no reference file exists) goes through the exact search and
+    equals the oracle on the same array."""
+    from gq_b200 import codebook_generator as G
+    cb = G.train_codebook(16, 512, train_size=20000, iter=4, objective="hsq")
+    assert cb.shape == (512, 16) and np.isfinite(cb).all()
+    assert abs(np.linalg.norm(cb, axis=1) - 1).max() < 1e-5
+    rnd = np.random.RandomState(0).standard_normal((512, 16)).astype(np.float32)
+    assert G.quantisation_error(cb, n=20000) < G.quantisation_error(rnd, n=20000)
+    big = O.normalize(np.random.RandomState(4).standard_normal((65536, 16)).astype(np.float32))[1]
+    x = gen_input(77, 16 * 3000)
+    n = 3000
+    codes = torch.empty(n, dtype=torch.int32, device=DEV)
+    u = torch.empty(n, device=DEV)
+    seg = torch.tensor([0, n], dtype=torch.int64, device=DEV)
+    ws = torch.empty(1 << 16, dtype=torch.uint8, device=DEV)
+    cbt = torch.from_numpy(big).to(DEV)
+    xt = torch.from_numpy(x).to(DEV)
+    _lib.call("gq_hsq_search", xt.data_ptr(), n, 16, cbt.data_ptr(), 65536, codes.data_ptr(), 4, u.data_ptr(),
+              seg.data_ptr(), 1, None, ws.data_ptr(), ws.numel(), _lib.ALGO_AUTO, _lib.stream())
+    torch.cuda.synchronize()
+    oc, ou = O.hsq_search(x.reshape(-1, 16), big)
+    assert np.array_equal(codes.cpu().numpy(), oc) and np.array_equal(u.cpu().numpy(), ou)

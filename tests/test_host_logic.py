@@ -148,3 +148,20 @@ def test_peer_records_row_and_address_arithmetic():
     assert offs[0] == 0 and offs[3] == (pr.base[3] + 3 * 4096) - pr.base[0]
     pr.step = 1                                                  # odd step: second half of the block
     assert pr.parity == 1 and pr.row() == 4 + 2 and pr.user0_record_ptr() == pr.base[0] + 4 * 4096
+
+
+def test_codebook_generator_small(tmp_path):
+    """gq_b200.codebook_generator: the reference's train_codebook / generate surface
+    (codebook_generator.py:14-31), files readable by fvecs_read and by load_codebook."""
+    from gq_b200 import codebook_generator as G
+    from gq_b200.utils.vecs_io import fvecs_read
+    cb = G.train_codebook(8, 32, train_size=4000, iter=5, device=torch.device("cpu"))
+    assert cb.shape == (32, 8) and cb.dtype == np.float32 and np.isfinite(cb).all()
+    again = G.train_codebook(8, 32, train_size=4000, iter=5, device=torch.device("cpu"))
+    assert np.array_equal(cb, again)                                  # deterministic for a seed
+    rnd = np.random.RandomState(0).standard_normal((32, 8)).astype(np.float32)
+    assert G.quantisation_error(cb, n=4000) < G.quantisation_error(rnd, n=4000)   # better than random directions
+    out = G.generate(dims=[4], Ks=[8], out_dir=str(tmp_path), train_size=500, iter=3)
+    assert len(out) == 1 and out[0].endswith("angular_dim_4_Ks_8.fvecs")
+    assert fvecs_read(out[0]).shape == (8, 4)
+    assert G.generate(dims=[4], Ks=[8], out_dir=str(tmp_path), train_size=500, iter=3) == []   # kept, not appended to
