@@ -91,7 +91,7 @@ size_t gq_hsq_encode_workspace_bytes(int64_t n_chunks, int d, int K, int n_seg)
 {
     (void)d; (void)K;
     size_t keys = align_up((size_t)(n_seg > 0 ? n_seg : 1) * 2 * sizeof(uint32_t), 256);
-    return keys + 256 /* grid barrier word */ + hsq_tc_workspace_bytes(n_chunks);
+    return keys + 256 /* grid barrier word */ + hsq_tc_workspace_bytes(n_chunks) + hsq_tck_workspace_bytes(d, K);
 }
 
 static int validate_group(const void *grad, int64_t n_chunks, int d, const void *codebook, int K,
@@ -119,11 +119,17 @@ int gq_hsq_search(const float *grad, int64_t n_chunks, int d, const float *codeb
     GQ_REQUIRE(((uintptr_t)grad & 15) == 0, "gradient must be 16-byte aligned");
     cudaStream_t st = as_stream(stream);
     const bool tc_ok = hsq_tc_supported(d, K, code_bytes);
-    if (algo == GQ_ALGO_TC && !tc_ok) {
-        set_error("tcgen05 search supports d == 16, K == 256, uint8 codes (got d=%d K=%d code_bytes=%d)",
+    const bool tck_ok = !tc_ok && hsq_tck_supported(d, K, code_bytes) && workspace != nullptr &&
+                        ((uintptr_t)workspace & 255) == 0 && workspace_bytes >= hsq_tck_workspace_bytes(d, K);
+    if (algo == GQ_ALGO_TC && !tc_ok && !tck_ok) {
+        set_error("tcgen05 search supports d == 16 with K == 256 (uint8 codes) or K = 512..4096, a multiple of 512 "
+                  "(int32 codes, workspace of gq_hsq_encode_workspace_bytes); got d=%d K=%d code_bytes=%d",
                   d, K, code_bytes);
         return GQ_ERR_UNSUPPORTED;
     }
+    if (tck_ok && algo != GQ_ALGO_EXACT && n_chunks > 0)
+        return hsq_search_tck(grad, n_chunks, codebook, K, codes, u_out, seg_start, n_seg, minmax_keys, workspace,
+                              workspace_bytes, st);
     if (tc_ok && algo != GQ_ALGO_EXACT && n_chunks > 0) {
         if (tc_generation() == 1)
             return hsq_search_tc(grad, n_chunks, d, codebook, K, codes, code_bytes, u_out, seg_start, n_seg,

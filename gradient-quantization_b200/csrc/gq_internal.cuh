@@ -63,6 +63,13 @@ int hsq_encode_tc_fused(const float *grad, int64_t n_chunks, const float *codebo
                         int n_bit, int random, const float *uniforms, uint64_t seed, uint64_t offset,
                         uint8_t *l, float *lbub, cudaStream_t st);
 
+// hsq_tck.cu: tcgen05 search for large codebooks (d == 16, K = 512..4096, int32 codes)
+bool hsq_tck_supported(int d, int K, int code_bytes);
+size_t hsq_tck_workspace_bytes(int d, int K);
+int hsq_search_tck(const float *grad, int64_t n_chunks, const float *codebook, int K, void *codes, float *u_out,
+                   const int64_t *seg_start, int n_seg, uint32_t *minmax_keys, void *workspace, size_t workspace_bytes,
+                   cudaStream_t st);
+
 int tc_generation();   // abi.cu: 1 = hsq_tc.cu + separate quantize launch, 2 (default) = hsq_tc2.cu
 
 // hsq_tc2.cu: second-generation tcgen05 encode (d == 16, K == 256, uint8 codes).  One launch does the
