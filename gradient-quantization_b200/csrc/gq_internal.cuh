@@ -34,7 +34,7 @@ __device__ __forceinline__ void rider_run(const Rider &r, int64_t tid, int64_t n
             }
         }
         if (r.mean) acc = __fdiv_rn(acc, (float)r.n_users);
-        if (r.accumulate) acc = __fadd_rn(r.out[i], acc);
+        if (r.accumulate) acc = (r.accumulate == 2) ? __fsub_rn(r.out[i], acc) : __fadd_rn(r.out[i], acc);
         r.out[i] = acc;
     }
 }

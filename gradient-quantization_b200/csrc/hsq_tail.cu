@@ -266,6 +266,19 @@ int launch_norm_dequantize(const void *l, int l_bytes, int64_t n, const int64_t 
     return GQ_OK;
 }
 
+// accumulate: 0 store the reduction r, 1 out = out + r (ring: grad += previous hop's sum,
+// ring_quantizer.py:31-32), 2 out = out - r (error feedback: error = grad - decompress(compress(grad)),
+// ps_quantizer.py:39, with `out` holding the compensated gradient)
+__device__ __forceinline__ float combine1(float o, float r, int accumulate)
+{
+    return accumulate == 2 ? __fsub_rn(o, r) : __fadd_rn(o, r);
+}
+__device__ __forceinline__ float4 combine4(float4 o, float4 r, int accumulate)
+{
+    return accumulate == 2 ? make_float4(__fsub_rn(o.x, r.x), __fsub_rn(o.y, r.y), __fsub_rn(o.z, r.z), __fsub_rn(o.w, r.w))
+                           : make_float4(__fadd_rn(o.x, r.x), __fadd_rn(o.y, r.y), __fadd_rn(o.z, r.z), __fadd_rn(o.w, r.w));
+}
+
 // ------------------------------------------------------- decode-and-reduce ---
 // One thread per float4 of the output, four independent float4 per thread (the loads of all
 // four are issued before any is consumed).  A chunk of D floats is D/4 consecutive float4, so
@@ -371,8 +384,7 @@ hsq_decode_reduce_kernel(const CodeT *__restrict__ codes, const LT *__restrict__
             }
             if (accumulate) {
                 const float4 o = o4[f[j]];
-                r.x = __fadd_rn(o.x, r.x); r.y = __fadd_rn(o.y, r.y);
-                r.z = __fadd_rn(o.z, r.z); r.w = __fadd_rn(o.w, r.w);
+                r = combine4(o, r, accumulate);
             }
             o4[f[j]] = r;
         }
@@ -413,7 +425,7 @@ hsq_decode_reduce_generic_kernel(const CodeT *__restrict__ codes, const LT *__re
             acc = (u == 0) ? pr : __fadd_rn(acc, pr);
         }
         if (mean) acc = __fdiv_rn(acc, (float)n_users);
-        if (accumulate) acc = __fadd_rn(out[e], acc);
+        if (accumulate) acc = combine1(out[e], acc, accumulate);
         out[e] = acc;
     }
 }
@@ -536,8 +548,7 @@ hsq_decode_reduce_warp_kernel(const CodeT *__restrict__ codes, const LT *__restr
                 }
                 if (accumulate) {
                     const float4 o = o4[f];
-                    acc.x = __fadd_rn(o.x, acc.x); acc.y = __fadd_rn(o.y, acc.y);
-                    acc.z = __fadd_rn(o.z, acc.z); acc.w = __fadd_rn(o.w, acc.w);
+                    acc = combine4(o, acc, accumulate);
                 }
                 o4[f] = acc;
             }
@@ -732,8 +743,7 @@ hsq_decode_reduce_staged_kernel(const uint8_t *__restrict__ codes, const uint8_t
                     }
                     if (accumulate) {
                         const float4 o = o4[f];
-                        acc.x = __fadd_rn(o.x, acc.x); acc.y = __fadd_rn(o.y, acc.y);
-                        acc.z = __fadd_rn(o.z, acc.z); acc.w = __fadd_rn(o.w, acc.w);
+                        acc = combine4(o, acc, accumulate);
                     }
                     o4[f] = acc;
                 }
@@ -912,7 +922,7 @@ f32_reduce_users_kernel(const float *__restrict__ in, int64_t user_stride, int n
             acc = __fadd_rn(acc, *reinterpret_cast<const float *>(
                                      reinterpret_cast<const char *>(in) + u * user_stride + 4 * i));
         if (mean) acc = __fdiv_rn(acc, (float)n_users);
-        if (accumulate) acc = __fadd_rn(out[i], acc);
+        if (accumulate) acc = combine1(out[i], acc, accumulate);
         out[i] = acc;
     }
 }
@@ -931,7 +941,7 @@ f32_reduce_users_scattered_kernel(const float *__restrict__ in, const UserOffset
             }
         }
         if (mean) acc = __fdiv_rn(acc, (float)n_users);
-        if (accumulate) acc = __fadd_rn(out[i], acc);
+        if (accumulate) acc = combine1(out[i], acc, accumulate);
         out[i] = acc;
     }
 }

@@ -199,7 +199,7 @@ qsgd_decode_reduce_kernel(const float *__restrict__ norm, const void *__restrict
             if (i0 + t >= n) continue;
             float r = acc[t];
             if (mean) r = __fdiv_rn(r, (float)n_users);
-            if (accumulate) r = __fadd_rn(out[i0 + t], r);
+            if (accumulate) r = (accumulate == 2) ? __fsub_rn(out[i0 + t], r) : __fadd_rn(out[i0 + t], r);
             out[i0 + t] = r;
         }
     }
@@ -304,7 +304,7 @@ sign_decode_reduce_kernel(const uint8_t *__restrict__ packed, int64_t user_strid
             if (i0 + t >= n) continue;
             float r = acc[t];
             if (mean) r = __fdiv_rn(r, (float)n_users);
-            if (accumulate) r = __fadd_rn(out[i0 + t], r);
+            if (accumulate) r = (accumulate == 2) ? __fsub_rn(out[i0 + t], r) : __fadd_rn(out[i0 + t], r);
             out[i0 + t] = r;
         }
     }

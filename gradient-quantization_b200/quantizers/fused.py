@@ -218,15 +218,17 @@ class FusedPlan:
                 return None
         return base if base % 256 == 0 else None
 
-    def gather(self, tensors, buf=None):
+    def gather(self, tensors, buf=None, feedback=0, scale=0.0):
         """Copy per-parameter gradients into the arena (skips views already in it): one
-        multi-tensor kernel (gq_gather_f32), the pointer table travels as its parameter."""
+        multi-tensor kernel (gq_gather_f32), the pointer table travels as its parameter.
+        feedback = 1 / 2: `buf` holds the user's error state and becomes grad + scale * error
+        (2: written back into the gradient tensors too) -- every tensor is then processed."""
         import ctypes
         buf = self.arena if buf is None else buf
         base = buf.data_ptr()
         ptrs, offs, sizes, keep = [], [], [], []
         for i, t in enumerate(tensors):
-            if t.data_ptr() == base + self.tensor_off[i] * 4:
+            if t.data_ptr() == base + self.tensor_off[i] * 4 and not feedback:
                 continue
             if t.dtype != torch.float32 or not t.is_contiguous():
                 t = _lib.f32c(t.detach())
@@ -238,7 +240,7 @@ class FusedPlan:
         n = len(ptrs)
         if n:
             _lib.call("gq_gather_f32", (ctypes.c_void_p * n)(*ptrs), (ctypes.c_int64 * n)(*offs),
-                      (ctypes.c_int64 * n)(*sizes), n, base, _lib.stream())
+                      (ctypes.c_int64 * n)(*sizes), n, base, int(feedback), float(scale), _lib.stream())
 
     def compressed_elems(self):
         return sum(g.n for g in self.groups if g.kind != "identity")
@@ -373,6 +375,11 @@ class FusedPlan:
         return (g.dim == 16 and g.K == 256 and g.code_bytes == 1 and g.n_bit <= 7 and g.l_bytes == 1
                 and g.n_seg <= 1024 and g.n_chunks > 0)
 
+    def supports_inplace_feedback(self):
+        """Error feedback without extra sweeps needs decode kernels with the subtract mode
+        (accumulate = 2): everything but the top-k scatter."""
+        return all(g.kind != "topk" for g in self.groups)
+
     def decode(self, first_user=0, n_users=None, mean=True, accumulate=False, out=None,
                base_ptr=None, user_offsets=None):
         """out (arena layout) = [out +] reduce over records[first_user : first_user+n_users].
@@ -382,7 +389,7 @@ class FusedPlan:
         n_users = self.n_users if n_users is None else n_users
         st = _lib.stream()
         mean = 1 if mean else 0
-        acc = 1 if accumulate else 0
+        acc = int(accumulate)            # 0 store, 1 out += decoded, 2 out -= decoded (error feedback)
         ident, carrier = self._rider_pair(n_users)
         if user_offsets is not None:
             for g in self.groups:

@@ -113,6 +113,16 @@ class PSQuantizer(QuantizerBase):
             if flat is not None:          # gradients already form one arena-shaped buffer: read in place
                 self._encode(slot, user, src=flat, uniforms=uniforms)
                 return
+        if self.error_feedback and plan.supports_inplace_feedback():
+            # The user's error state E_u (arena layout) becomes g + scale * E_u inside the gather kernel
+            # (ps_quantizer.py:35; written back into param.grad too, which the reference mutates in
+            # place), is encoded in place, and the decode of the fresh record subtracts itself from
+            # it: E_u = g' - decompress(compress(g'))  (:36-39).  No axpy / sub sweeps, no scratch arena.
+            err = self._ef_buffers(user)
+            plan.gather(grads, buf=err, feedback=2, scale=scale)
+            self._encode(slot, user, src=err, uniforms=uniforms)
+            plan.decode(first_user=slot, n_users=1, mean=False, accumulate=2, out=err)
+            return
         plan.gather(grads)
         if self.error_feedback:
             err = self._ef_buffers(user)
@@ -220,6 +230,18 @@ class PSQuantizer(QuantizerBase):
         every rank computes the same result."""
         p2 = self.phase2_plan()
         n = g.numel()
+        if self.error_feedback and p2.supports_inplace_feedback():
+            # server_error S becomes g + S (ps_quantizer.py:54), is compressed, and the decode of that
+            # record is both stored as the new gradient and subtracted from S (S = g' - D, :57)
+            if not hasattr(self, "_server_err"):
+                self._server_err = torch.zeros_like(g)
+                for p, v in zip(self.parameters, self.plan.views(self._server_err)):
+                    p.server_error = v
+            p2.gather(self.plan.views(g), buf=self._server_err, feedback=1, scale=1.0)
+            p2.encode(0, src=self._server_err, uniforms=uniforms, shared_rng=True)
+            p2.decode(mean=False, out=g)
+            p2.decode(mean=False, accumulate=2, out=self._server_err)
+            return g
         if self.error_feedback:
             if not hasattr(self, "_server_err"):
                 self._server_err = torch.zeros_like(g)

@@ -34,16 +34,25 @@ class RingQuantizer(QuantizerBase):
             # grad += previous hop's decompressed running sum   (ring_quantizer.py:31-32)
             plan.decode(first_user=user - 1, n_users=1, mean=False, accumulate=True, out=plan.arena)
         n = plan.arena.numel()
-        if self.error_feedback:
+        if self.error_feedback and plan.supports_inplace_feedback():
+            # E_u = (grad + previous) + scale * E_u in one multi-tensor pass over the arena's views
+            # (same order of additions as ring_quantizer.py:32-34), encoded in place, and the decode of
+            # the fresh record subtracts itself: E_u = grad' - decompress(compress(grad'))  (:36-38)
+            err = self._ef_buffers(user)
+            plan.gather(plan.views(), buf=err, feedback=1, scale=scale)
+            plan.encode(user, src=err, uniforms=uniforms, rng_user=user)
+            plan.decode(first_user=user, n_users=1, mean=False, accumulate=2, out=err)
+        elif self.error_feedback:
             err = self._ef_buffers(user)
             _lib.call("gq_axpy", _lib.ptr(plan.arena), _lib.ptr(err), float(scale), n,
                       _lib.ptr(plan.arena), _lib.stream())
-        plan.encode(user, uniforms=uniforms, rng_user=user)
-        if self.error_feedback:
+            plan.encode(user, uniforms=uniforms, rng_user=user)
             if not hasattr(self, "_scratch_buf"):
                 self._scratch_buf = torch.empty_like(plan.arena)
             dec = plan.decode(first_user=user, n_users=1, mean=False, out=self._scratch_buf)
             _lib.call("gq_sub", _lib.ptr(plan.arena), _lib.ptr(dec), n, _lib.ptr(err), _lib.stream())
+        else:
+            plan.encode(user, uniforms=uniforms, rng_user=user)
         if self.distributed:
             xch.ring_send_next(plan.records, user, self.world)
 

@@ -126,7 +126,8 @@ int gq_norm_dequantize(const void *l, int l_bytes, int64_t n, const int64_t *seg
  * n_bit == 32, `l` is unused and norms_f32 (+ u*user_stride_bytes) holds fp32 norms.
  *   r[i]   = sum_{u=0..U-1} codebook[code_u[c], j] * norm_u[c]   (user order)
  *   mean   : r /= U                 (true division)
- *   out[i] = accumulate ? out[i] + r[i] : r[i]
+ *   out[i] = r[i] (accumulate 0), out[i] + r[i] (1), out[i] - r[i] (2: error feedback,
+ *            error = grad - decompress(compress(grad)), ps_quantizer.py:39)
  */
 int gq_hsq_decode_reduce(const void *codes, int code_bytes, const void *l, int l_bytes,
                          const float *lbub, const float *norms_f32,
@@ -240,9 +241,14 @@ int gq_hsq_tc_debug(const float *grad, int64_t n_chunks, const float *codebook, 
  * sizes in elements) to dst + dst_offsets[t] (elements) -- how the per-parameter gradients of
  * main.py:229-230 (param.grad after loss.backward()) reach the codec arena that
  * PSQuantizer.record / RingQuantizer.record (quantizers/ps_quantizer.py:33-44) encode from.
- * One launch per 128 tensors; the pointer table travels as a kernel parameter. */
+ * One launch per 128 tensors; the pointer table travels as a kernel parameter.
+ * feedback = 1: dst holds the user's error state e and becomes src + scale * e
+ *   (`grad += scale * error`, ps_quantizer.py:35 / ring_quantizer.py:34, same two roundings);
+ * feedback = 2: that sum is also written back to the source tensors (the reference mutates
+ *   param.grad in place).  The decode entry points' accumulate = 2 (out = out - decoded) then turn
+ *   the same buffer into the new error (ps_quantizer.py:39) without another sweep. */
 int gq_gather_f32(const void *const *src_ptrs, const int64_t *dst_offsets, const int64_t *sizes,
-                  int n_tensors, float *dst, gq_stream_t stream);
+                  int n_tensors, float *dst, int feedback, float scale, gq_stream_t stream);
 
 /* Diagnostic hook for the second-generation tcgen05 kernel: search only, and CTA 0 time-stamps
  * the pipeline events of its first 128 tiles into trace (device int64 [9 * 128], clock64 values;
