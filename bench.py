@@ -208,13 +208,54 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+ORIG_AFFINITY = None
+
+
+def bind_to_gpu_numa(index):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned host buffer
+    is allocated (first touch then places the pages there).  Round 1's end-to-end number did not
+    scale (46 -> 8 GB/s per GPU from N = 1 to 8) because every rank's pinned buffers sat on node 0.
+    Returns a short description for the JSON line; never fails the run."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        bdf = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bdf = (bdf.decode() if isinstance(bdf, bytes) else bdf).lower()
+        if len(bdf.split(":")[0]) == 8:          # nvml pads the domain to 8 hex digits, sysfs uses 4
+            bdf = bdf[4:]
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as fh:
+            node = int(fh.read().strip())
+        if node < 0:
+            return "numa node unknown"
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as fh:
+            cpus = set()
+            for part in fh.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        global ORIG_AFFINITY
+        ORIG_AFFINITY = set(os.sched_getaffinity(0))
+        allowed = cpus & ORIG_AFFINITY
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return "bound to NUMA node %d (%d cpus)" % (node, len(allowed))
+    except Exception as e:  # noqa: BLE001
+        return "not bound (%s)" % type(e).__name__
+
+
 # ----------------------------------------------------------- CPU baselines ---
 def host_threads():
     return os.cpu_count() or 1
 
 
 def use_all_host_threads():
-    """torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm must not inherit that."""
+    """torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm must not inherit that
+    (nor the NUMA binding the GPU arm gave itself)."""
+    if ORIG_AFFINITY:
+        try:
+            os.sched_setaffinity(0, ORIG_AFFINITY)
+        except Exception:  # noqa: BLE001
+            pass
     n = host_threads()
     os.environ["OMP_NUM_THREADS"] = str(n)
     os.environ.pop("OMP_THREAD_LIMIT", None)
@@ -359,6 +400,7 @@ def main():
     if world != a.gpus and a.gpus > 1:
         raise SystemExit("bench.py --gpus %d needs WORLD_SIZE == %d (launch with torch.distributed.run)"
                          % (a.gpus, a.gpus))
+    numa = bind_to_gpu_numa(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -596,7 +638,8 @@ def main():
                 "api": "Quantizer.record(rank)/apply() on ordinary per-parameter .grad tensors (model order, copied "
                        "from pinned host memory each step; record() gathers them into the codec arena with one "
                        "multi-tensor kernel), averaged gradient copied back to pinned host memory each step",
-                "pipelining": "double-buffered: H2D of step i+1 and D2H of step i-1 overlap step i"},
+                "pipelining": "double-buffered: H2D of step i+1 and D2H of step i-1 overlap step i",
+                "host": numa},
         "gpu_launches": K * q.launches_per_step(),
         "clocks": clocks,
     }
