@@ -69,7 +69,8 @@ _SIGNATURES = {
                               c_int, c_void_p, c_void_p]),
     "gq_hsq_tc_debug": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
                                 c_int, c_void_p]),
-    "gq_hsq_tc2_trace": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "gq_hsq_tc2_trace": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_void_p]),
     "gq_gather_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_float, c_void_p]),
     "gq_axpy": (c_int, [c_void_p, c_void_p, c_float, c_i64, c_void_p, c_void_p]),
     "gq_sub": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_void_p]),

@@ -143,11 +143,19 @@ int gq_hsq_search(const float *grad, int64_t n_chunks, int d, const float *codeb
 }
 
 int gq_hsq_tc2_trace(const float *grad, int64_t n_chunks, const float *codebook, void *codes, float *u_out,
-                     int64_t *trace, gq_stream_t stream)
+                     const int64_t *seg_start, int n_seg, void *l, float *lbub, void *workspace, int64_t *trace,
+                     gq_stream_t stream)
 {
     GQ_REQUIRE(hsq_tc_supported(16, 256, 1), "tcgen05 search needs an sm_100 device");
-    return hsq_search_tc2_trace(grad, n_chunks, codebook, codes, u_out, reinterpret_cast<long long *>(trace),
-                                as_stream(stream));
+    if (l == nullptr)
+        return hsq_tc2_trace(grad, n_chunks, codebook, codes, u_out, nullptr, 0, nullptr, nullptr, nullptr, nullptr,
+                             reinterpret_cast<long long *>(trace), as_stream(stream));
+    GQ_REQUIRE(seg_start && n_seg >= 1 && lbub && workspace && ((uintptr_t)workspace & 255) == 0, "bad arguments");
+    uint32_t *keys = reinterpret_cast<uint32_t *>(workspace);
+    uint32_t *barrier = reinterpret_cast<uint32_t *>((char *)workspace + align_up((size_t)n_seg * 8, 256));
+    Tc2Tail tail = {(uint8_t *)l, lbub, nullptr, 1234u, 0u, 6, 1};
+    return hsq_tc2_trace(grad, n_chunks, codebook, codes, u_out, seg_start, n_seg, keys, reinterpret_cast<uint64_t *>(barrier) + 1,
+                         barrier, &tail, reinterpret_cast<long long *>(trace), as_stream(stream));
 }
 
 int gq_norm_quantize(const float *u, int64_t n, const int64_t *seg_start, int n_seg, int n_bit,

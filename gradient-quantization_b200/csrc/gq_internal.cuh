@@ -98,8 +98,9 @@ bool hsq_tc2_tail_supported(int n_seg, int n_bit, int l_bytes, const void *u_out
 int hsq_encode_tc2(const float *grad, int64_t n_chunks, const float *codebook, void *codes, float *u_out,
                    const int64_t *seg_start, int n_seg, uint32_t *keys, uint64_t *flag, uint32_t *barrier,
                    const Rider &rider, const Tc2Tail *tail, const Tc2Remote *remote, cudaStream_t st);
-int hsq_search_tc2_trace(const float *grad, int64_t n_chunks, const float *codebook, void *codes, float *u_out,
-                         long long *trace, cudaStream_t st);
+int hsq_tc2_trace(const float *grad, int64_t n_chunks, const float *codebook, void *codes, float *u_out,
+                  const int64_t *seg_start, int n_seg, uint32_t *keys, uint64_t *flag, uint32_t *barrier,
+                  const Tc2Tail *tail, long long *trace, cudaStream_t st);
 // thread-local pending remote delivery of the calling host thread, consumed by the next gq_hsq_encode
 Tc2Remote take_remote();
 void set_remote(const Tc2Remote &r);

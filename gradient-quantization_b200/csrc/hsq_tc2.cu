@@ -193,11 +193,11 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
     const uint32_t bar_full = smem_u32(bars);
     const uint32_t bar_empty = bar_full + 8 * kStages;
     const uint32_t bar_tfull = bar_empty + 8 * kStages;
-    uint32_t *s_rel = reinterpret_cast<uint32_t *>(smem + L::kOffBar + 8 * (3 * kStages));   // [2] first-pass arrivals per TMEM buffer
+    const uint32_t bar_tempty = bar_tfull + 8 * kStages;
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(smem + L::kOffBar + 8 * (4 * kStages));
     float *s_cn = reinterpret_cast<float *>(smem + L::kOffBar + 8 * (4 * kStages) + 8);   // [8] per-warp norm maxima
     int *s_misc = reinterpret_cast<int *>(smem + L::kOffBar + 8 * (4 * kStages) + 8 + 32);
-    static_assert(8 * (4 * kStages) + 8 + 32 + 16 <= 512 && 8 * (3 * kStages) + 8 <= 8 * (4 * kStages), "barrier region");
+    static_assert(8 * (4 * kStages) + 8 + 32 + 16 <= 512, "barrier region");
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -212,9 +212,8 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
             mbar_init(bar_full + 8 * s, 1);
             mbar_init(bar_empty + 8 * s, 4);
             mbar_init(bar_tfull + 8 * s, 1);
+            mbar_init(bar_tempty + 8 * s, 4);
         }
-        s_rel[0] = 0u;
-        s_rel[1] = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -300,6 +299,10 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
     // (a non-finite codebook gives margin = +inf: threshold -inf / NaN, every group is rescored)
     const float margin = (PAIR ? kMarginPair : kMargin) * (1.0f + 1.0e-5f) * cn;
     pdl_wait();
+    // TRACE: per-CTA wall-clock stamps (ns) after the trace table: start, main loop done, grid barrier passed, tail done
+#define GQ_STAMP(k) do { if (TRACE && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); \
+        P.trace[9 * 128 + 4 * blockIdx.x + (k)] = (long long)t_; } } while (0)
+    GQ_STAMP(0);
 
     if (warp == 0) {
         // ------------------------------------------------------ TMA producer ---
@@ -314,17 +317,20 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
         }
     } else if (warp == 1) {
         // -------------------------------------------------------- MMA issuer ---
-        // Only the first two tiles are issued here.  Afterwards the MMA of local tile it + 2 is issued by
-        // whichever epilogue warp is the LAST of its group to finish reading TMEM buffer it & 1 (arrival
-        // counter in shared memory): a dedicated issuer warp sleeping on an mbarrier took ~1000 cycles
-        // from the release to the issue, and that turnaround (first pass + release -> issue -> accumulators
-        // seen), not the epilogue arithmetic, set the tile period (tests/tc2_trace.py).
+        // (Issuing the MMA of tile it + 2 from the last epilogue warp to leave the TMEM buffer instead of
+        //  from this warp removes ~900 cycles between release and issue -- and was measured SLOWER, 64 vs
+        //  56 us: the buffer turnaround is set by the slowest of the group's four warps in the first pass,
+        //  ~1500 cycles under contention with the other groups' rescoring, and an MMA running against the
+        //  other group's TMEM loads costs them more than the early issue gains; tests/tc2_trace.py.)
         if (lane == 0) {
-            for (int it = 0; it < my_tiles && it < 2; ++it) {
-                mbar_wait_sleep(bar_full + 8 * it, 0);
+            for (int it = 0; it < my_tiles; ++it) {
+                const int s = it % kStages;
+                const int b = it & 1;
+                if (it >= 2) mbar_wait_sleep(bar_tempty + 8 * ((it - 2) % kStages), ((it - 2) / kStages) & 1);
+                mbar_wait_sleep(bar_full + 8 * s, (it / kStages) & 1);
                 tc_fence_after();
-                issue_tile_mma(smem_u32(s_a + it * kTileBytes), smem_u32(s_cb), tmem_base + (uint32_t)(it * kK),
-                               bar_tfull + 8 * it);
+                issue_tile_mma(smem_u32(s_a + s * kTileBytes), smem_u32(s_cb), tmem_base + (uint32_t)(b * kK),
+                               bar_tfull + 8 * s);
                 GQ_TRACE(1, it);
             }
         }
@@ -414,26 +420,10 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
                     if (h + 1 < kK / 32) tmem_ld_wait16(sa);
                 }
             }
-            // TMEM buffer b may be overwritten by the MMA of local tile it + 2: the last of the group's four
-            // warps to get here issues it.  The counter is a RELAXED shared-memory atomic: every warp's TMEM
-            // loads have completed (tcgen05.wait::ld) before its increment is issued, and the tcgen05
-            // before/after_thread_sync fences order the asynchronous tensor-core accesses around it; an
-            // acq_rel atomic costs a MEMBAR that waits for the previous tile's global stores (+700 cycles).
+            // TMEM buffer b may be overwritten by the MMA of local tile it + 2
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) {
-                const uint32_t old = atomicAdd(s_rel + b, 1u);
-                const int nt = it + 2;
-                if ((old & 3u) == 3u && nt < my_tiles) {
-                    const int ns = nt % kStages;
-                    mbar_wait(bar_full + 8 * ns, (nt / kStages) & 1);   // the TMA ring runs several tiles ahead
-                    tc_fence_after();
-                    issue_tile_mma(smem_u32(s_a + ns * kTileBytes), smem_u32(s_cb), tmem_base + (uint32_t)(b * kK),
-                                   bar_tfull + 8 * ns);
-                    GQ_TRACE(1, nt);
-                }
-            }
-            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * s);
             if (tracer) GQ_TRACE(3, it);
 
             // ---- this row's chunk, from the (swizzled) smem tile
@@ -645,6 +635,7 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
     if (warp == 2) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
     }
+    GQ_STAMP(1);
     if (P.l == nullptr) return;
 
     // =============================================== fused tail: n-bit norm quantization ===
@@ -660,6 +651,7 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
         } while (++spins < (1u << 24));
         if (seen < gridDim.x) __trap();
     }
+    GQ_STAMP(2);
     const int n_seg = P.n_seg;
     int *s_seg = reinterpret_cast<int *>(smem + L::kOffA);                                   // [n_seg + 1]
     float2 *s_lbub = reinterpret_cast<float2 *>(smem + L::kOffA + 4 * ((n_seg + 2) & ~1));   // [n_seg]
@@ -787,6 +779,8 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
             }
         }
     }
+    if (TRACE) __syncthreads();
+    GQ_STAMP(3);
     if (R.n > 0) {
         // identity section (written by the riders of all CTAs before the grid barrier), then the
         // delivery handshake: the last CTA to finish announces the epoch to every rank
@@ -907,9 +901,11 @@ static int launch_variant(const Variant &v, const CUtensorMap &mg, const Enc2 &P
 
 }  // namespace tc2
 
-// search only, default variant, with the pipeline trace of CTA 0 (9 x 128 int64, device)
-int hsq_search_tc2_trace(const float *grad, int64_t n_chunks, const float *codebook, void *codes, float *u_out,
-                         long long *trace, cudaStream_t st)
+// default variant with the pipeline trace of CTA 0 (9 x 128 int64) followed by four wall-clock stamps
+// per CTA (4 x grid int64); search only, or the whole one-launch encode when `tail` is given
+int hsq_tc2_trace(const float *grad, int64_t n_chunks, const float *codebook, void *codes, float *u_out,
+                  const int64_t *seg_start, int n_seg, uint32_t *keys, uint64_t *flag, uint32_t *barrier,
+                  const Tc2Tail *tail, long long *trace, cudaStream_t st)
 {
     using namespace tc2;
     GQ_REQUIRE(((uintptr_t)grad & 15) == 0 && ((uintptr_t)codebook & 15) == 0, "TMA needs 16-byte aligned bases");
@@ -917,12 +913,28 @@ int hsq_search_tc2_trace(const float *grad, int64_t n_chunks, const float *codeb
     CUtensorMap mg;
     int e = make_map(&mg, grad, n_chunks);
     if (e) return e;
+    static std::atomic<unsigned long long> counter{0x7ace000000000000ull};
     Enc2 P = {};
     P.codebook = codebook;
     P.n_chunks = (int)n_chunks;
     P.codes = (uint8_t *)codes;
     P.u_out = u_out;
     P.trace = trace;
+    if (tail != nullptr) {
+        P.seg_start = seg_start;
+        P.n_seg = n_seg;
+        P.keys = keys;
+        P.flag = reinterpret_cast<unsigned long long *>(flag);
+        P.id = counter.fetch_add(1) + 1;
+        P.l = tail->l;
+        P.lbub = tail->lbub;
+        P.barrier = barrier;
+        P.uniforms = tail->uniforms;
+        P.seed = tail->seed;
+        P.offset = tail->offset;
+        P.s = (float)(1u << tail->n_bit);
+        P.random = tail->random;
+    }
     const int n_tiles = (int)((n_chunks + kTileM - 1) / kTileM);
     int sms = sm_count();
     if (const char *g = getenv("GQ_TC_GRID")) {
@@ -940,7 +952,7 @@ int hsq_search_tc2_trace(const float *grad, int64_t n_chunks, const float *codeb
     else if (v.r2) e = launch(hsq_encode_tc2_kernel<3, true, true, true, true, true>, 512, Layout<3>::kSmemBytes);
     else e = launch(hsq_encode_tc2_kernel<3, true, true, true, false, true>, 512, Layout<3>::kSmemBytes);
     if (e) return e;
-    GQ_LAUNCH_CHECK("hsq_search_tc2_trace");
+    GQ_LAUNCH_CHECK("hsq_tc2_trace");
     return GQ_OK;
 }
 

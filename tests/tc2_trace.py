@@ -27,12 +27,29 @@ n = 1468652
 xs = [torch.randn(n * 16, device=dev) * 0.01 for _ in range(3)]
 codes = torch.empty(n, dtype=torch.uint8, device=dev)
 u = torch.empty(n, device=dev)
-trace = torch.zeros(9 * 128, dtype=torch.int64, device=dev)
+GRID = 148
+trace = torch.zeros(9 * 128 + 4 * GRID, dtype=torch.int64, device=dev)
+full = "--encode" in sys.argv
+lv = torch.empty(n, dtype=torch.uint8, device=dev)
+# a ResNet-50-like segment table: 76 tensors of equal size
+n_seg = 76
+seg = torch.tensor([n * i // n_seg // 4 * 4 for i in range(n_seg)] + [n], dtype=torch.int64, device=dev)
+lbub = torch.empty(2 * n_seg, device=dev)
+ws = torch.zeros(1 << 16, dtype=torch.uint8, device=dev)
 for i in range(3):
-    _lib.call("gq_hsq_tc2_trace", xs[i].data_ptr(), n, cbt.data_ptr(), codes.data_ptr(), u.data_ptr(), trace.data_ptr(),
-              _lib.stream())
+    _lib.call("gq_hsq_tc2_trace", xs[i].data_ptr(), n, cbt.data_ptr(), codes.data_ptr(), u.data_ptr(), seg.data_ptr(), n_seg,
+              lv.data_ptr() if full else None, lbub.data_ptr(), ws.data_ptr(), trace.data_ptr(), _lib.stream())
 torch.cuda.synchronize()
-t = trace.cpu().numpy().reshape(9, 128).astype(np.int64)
+raw = trace.cpu().numpy().astype(np.int64)
+t = raw[:9 * 128].reshape(9, 128)
+st = raw[9 * 128:].reshape(GRID, 4)
+st = st[st[:, 0] > 0]
+t_first = st[:, 0].min()
+print("per-CTA wall clock (us since the first CTA started), %d CTAs%s:" % (st.shape[0], " [whole encode]" if full else " [search only]"))
+for k, nm in enumerate(["start", "main loop done", "grid barrier passed", "tail done"]):
+    col = (st[:, k] - t_first) / 1e3
+    if (st[:, k] > 0).all():
+        print("  %-20s min %7.2f  median %7.2f  max %7.2f" % (nm, col.min(), np.median(col), col.max()))
 tiles = 77
 t0 = t[0, 0]
 ev = (t[:8, :tiles] - t0)
