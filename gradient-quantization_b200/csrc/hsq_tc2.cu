@@ -639,10 +639,128 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
     if (P.l == nullptr) return;
 
     // =============================================== fused tail: n-bit norm quantization ===
-    // grid barrier: every CTA's min/max atomics are performed before anyone reads lb/ub
+    // Grid barrier: every CTA's min/max atomics are performed before anyone reads lb/ub.  A CTA arrives,
+    // then does everything that does not depend on lb/ub WHILE it waits for the slower CTAs: the
+    // segment table, the loads of its own u values (and codes / uniforms) and the Philox draws.
     if (threadIdx.x == 0) {
         __threadfence();
         atomicAdd(P.barrier, 1u);
+    }
+    const int n_seg = P.n_seg;
+    int *s_seg = reinterpret_cast<int *>(smem + L::kOffA);                                   // [n_seg + 1]
+    float2 *s_lbub = reinterpret_cast<float2 *>(smem + L::kOffA + 4 * ((n_seg + 2) & ~1));   // [n_seg]
+    for (int i = threadIdx.x; i <= n_seg; i += kThreads) s_seg[i] = (int)P.seg_start[i];
+    const Remote &R = P.remote;
+    const int c_begin = tile0 * kTileM;
+    const int c_end = min((tile0 + my_tiles) * kTileM, n_chunks);
+    const int qb = c_begin >> 2, qe = (c_end + 3) >> 2;
+    const float s = P.s;
+    const int random = P.random;
+    const bool ext = random && P.uniforms != nullptr;
+    const bool philox = random && P.uniforms == nullptr;
+    const bool philox_aligned = (P.offset & 3u) == 0;
+    constexpr int J = 5;   // float4 groups per thread and pass: 512 threads x 5 x 4 = 10240 chunks >= 78 tiles
+    // u (and codes / uniforms / Philox draws) of up to J groups of four chunks, q0, q0 + kThreads, ...
+    auto load_pass = [&](int q0, float4 (&xv)[J], float4 (&rv)[J], uint32_t (&cw)[J]) {
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const int q = q0 + j * kThreads;
+            xv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            rv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            cw[j] = 0u;
+            if (q < qe) {
+                if (q * 4 + 3 < n_chunks) {
+                    xv[j] = __ldcg(reinterpret_cast<const float4 *>(P.u_out) + q);
+                    if (ext) rv[j] = __ldg(reinterpret_cast<const float4 *>(P.uniforms) + q);
+                    if (R.n > 0) cw[j] = __ldcg(reinterpret_cast<const uint32_t *>(P.codes) + q);
+                } else {
+                    float x[4] = {0.f, 0.f, 0.f, 0.f}, r[4] = {0.f, 0.f, 0.f, 0.f};
+                    for (int t = 0; t < 4; ++t) {
+                        if (q * 4 + t < n_chunks) {
+                            x[t] = __ldcg(P.u_out + q * 4 + t);
+                            if (ext) r[t] = __ldg(P.uniforms + q * 4 + t);
+                            if (R.n > 0) cw[j] |= (uint32_t)__ldcg(P.codes + q * 4 + t) << (8 * t);
+                        }
+                    }
+                    xv[j] = make_float4(x[0], x[1], x[2], x[3]);
+                    rv[j] = make_float4(r[0], r[1], r[2], r[3]);
+                }
+            }
+        }
+        if (philox) {
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                const int q = q0 + j * kThreads;
+                if (q >= qe) continue;
+                const int i0 = q * 4;
+                if (philox_aligned) {
+                    const uint4 w = philox4x32_10(P.seed, (P.offset + (uint64_t)i0) >> 2);
+                    rv[j] = make_float4(u01(w.x), u01(w.y), u01(w.z), u01(w.w));
+                } else {
+                    rv[j] = make_float4(philox_uniform(P.seed, P.offset, (uint64_t)i0), philox_uniform(P.seed, P.offset, (uint64_t)(i0 + 1)),
+                                        philox_uniform(P.seed, P.offset, (uint64_t)(i0 + 2)), philox_uniform(P.seed, P.offset, (uint64_t)(i0 + 3)));
+                }
+            }
+        }
+    };
+    // levels of those groups (needs lb/ub: after the barrier), stored locally and at the remote copies
+    auto finish_pass = [&](int q0, const float4 (&xv)[J], const float4 (&rv)[J], const uint32_t (&cw)[J], int &seg) {
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const int q = q0 + j * kThreads;
+            if (q >= qe) continue;
+            const int i0 = q * 4;
+            const float x[4] = {xv[j].x, xv[j].y, xv[j].z, xv[j].w};
+            const float r[4] = {rv[j].x, rv[j].y, rv[j].z, rv[j].w};
+            while (i0 >= s_seg[seg + 1]) ++seg;
+            int lv[4];
+            if (i0 + 3 < s_seg[seg + 1]) {   // all four chunks in one tensor
+                const float2 bb = s_lbub[seg];
+                if (bb.x - bb.y == 0.0f) {
+                    lv[0] = lv[1] = lv[2] = lv[3] = 0;
+                } else {
+                    const float den = __fsub_rn(bb.y, bb.x);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const float scaled = fabsf(__fdiv_rn(__fsub_rn(x[t], bb.x), den)) * s;
+                        const float cl = fminf(fmaxf(scaled, 0.0f), s - 1.0f);
+                        int li = (int)cl;
+                        if (random) li += (__fsub_rn(scaled, (float)li) > r[t]) ? 1 : 0;
+                        lv[t] = li;
+                    }
+                }
+            } else {
+                int sg = seg;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int i = i0 + t;
+                    if (i < n_chunks) {
+                        while (i >= s_seg[sg + 1]) ++sg;
+                        const float2 bb = s_lbub[sg];
+                        lv[t] = psc_level(x[t], bb.x, bb.y, s, random, r[t]);
+                    } else {
+                        lv[t] = 0;
+                    }
+                }
+            }
+            const uint32_t packed = (uint32_t)lv[0] | ((uint32_t)lv[1] << 8) | ((uint32_t)lv[2] << 16) | ((uint32_t)lv[3] << 24);
+            if (i0 + 3 < n_chunks) {
+                reinterpret_cast<uint32_t *>(P.l)[q] = packed;
+            } else {
+                for (int t = 0; t < 4; ++t)
+                    if (i0 + t < n_chunks) P.l[i0 + t] = (uint8_t)lv[t];
+            }
+            if (R.n > 0) {   // the record sections are padded to 256 bytes: whole words may be written remotely
+                remote_st32(R, reinterpret_cast<uint32_t *>(P.l) + q, packed);
+                remote_st32(R, reinterpret_cast<uint32_t *>(P.codes) + q, cw[j]);
+            }
+        }
+    };
+    float4 xv[J], rv[J];
+    uint32_t cw[J];
+    int q0 = qb + (int)threadIdx.x;
+    load_pass(q0, xv, rv, cw);
+    if (threadIdx.x == 0) {
         uint32_t seen, spins = 0;
         do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(P.barrier) : "memory");
@@ -651,13 +769,8 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
         } while (++spins < (1u << 24));
         if (seen < gridDim.x) __trap();
     }
-    GQ_STAMP(2);
-    const int n_seg = P.n_seg;
-    int *s_seg = reinterpret_cast<int *>(smem + L::kOffA);                                   // [n_seg + 1]
-    float2 *s_lbub = reinterpret_cast<float2 *>(smem + L::kOffA + 4 * ((n_seg + 2) & ~1));   // [n_seg]
-    for (int i = threadIdx.x; i <= n_seg; i += kThreads) s_seg[i] = (int)P.seg_start[i];
     __syncthreads();
-    const Remote &R = P.remote;
+    GQ_STAMP(2);
     for (int i = threadIdx.x; i < n_seg; i += kThreads) {
         const float lb = key_to_float(__ldcg(P.keys + 2 * i)), ub = key_to_float(__ldcg(P.keys + 2 * i + 1));
         s_lbub[i] = make_float2(lb, ub);
@@ -672,15 +785,6 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
     }
     __syncthreads();
     {
-        const int c_begin = tile0 * kTileM;
-        const int c_end = min((tile0 + my_tiles) * kTileM, n_chunks);
-        const int qb = c_begin >> 2, qe = (c_end + 3) >> 2;
-        const float s = P.s;
-        const int random = P.random;
-        const bool ext = random && P.uniforms != nullptr;
-        const bool philox = random && P.uniforms == nullptr;
-        const bool philox_aligned = (P.offset & 3u) == 0;
-        constexpr int J = 5;   // float4 groups per thread and pass: 512 threads x 5 x 4 = 10240 chunks >= 78 tiles
         int seg = 0;
         {   // segment of this CTA's first chunk (binary search in shared memory)
             int lo = 0, hi = n_seg;
@@ -690,93 +794,10 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
             }
             seg = lo;
         }
-        for (int q0 = qb + (int)threadIdx.x; q0 < qe; q0 += J * kThreads) {
-            float4 xv[J], rv[J];
-            uint32_t cw[J];
-#pragma unroll
-            for (int j = 0; j < J; ++j) {
-                const int q = q0 + j * kThreads;
-                xv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                rv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                cw[j] = 0u;
-                if (q < qe) {
-                    if (q * 4 + 3 < n_chunks) {
-                        xv[j] = __ldcg(reinterpret_cast<const float4 *>(P.u_out) + q);
-                        if (ext) rv[j] = __ldg(reinterpret_cast<const float4 *>(P.uniforms) + q);
-                        if (R.n > 0) cw[j] = __ldcg(reinterpret_cast<const uint32_t *>(P.codes) + q);
-                    } else {
-                        float x[4] = {0.f, 0.f, 0.f, 0.f}, r[4] = {0.f, 0.f, 0.f, 0.f};
-                        for (int t = 0; t < 4; ++t) {
-                            if (q * 4 + t < n_chunks) {
-                                x[t] = __ldcg(P.u_out + q * 4 + t);
-                                if (ext) r[t] = __ldg(P.uniforms + q * 4 + t);
-                                if (R.n > 0) cw[j] |= (uint32_t)__ldcg(P.codes + q * 4 + t) << (8 * t);
-                            }
-                        }
-                        xv[j] = make_float4(x[0], x[1], x[2], x[3]);
-                        rv[j] = make_float4(r[0], r[1], r[2], r[3]);
-                    }
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < J; ++j) {
-                const int q = q0 + j * kThreads;
-                if (q >= qe) continue;
-                const int i0 = q * 4;
-                const float x[4] = {xv[j].x, xv[j].y, xv[j].z, xv[j].w};
-                float r[4] = {rv[j].x, rv[j].y, rv[j].z, rv[j].w};
-                if (philox) {
-                    if (philox_aligned) {
-                        const uint4 w = philox4x32_10(P.seed, (P.offset + (uint64_t)i0) >> 2);
-                        r[0] = u01(w.x); r[1] = u01(w.y); r[2] = u01(w.z); r[3] = u01(w.w);
-                    } else {
-#pragma unroll
-                        for (int t = 0; t < 4; ++t) r[t] = philox_uniform(P.seed, P.offset, (uint64_t)(i0 + t));
-                    }
-                }
-                while (i0 >= s_seg[seg + 1]) ++seg;
-                int lv[4];
-                if (i0 + 3 < s_seg[seg + 1]) {   // all four chunks in one tensor
-                    const float2 bb = s_lbub[seg];
-                    if (bb.x - bb.y == 0.0f) {
-                        lv[0] = lv[1] = lv[2] = lv[3] = 0;
-                    } else {
-                        const float den = __fsub_rn(bb.y, bb.x);
-#pragma unroll
-                        for (int t = 0; t < 4; ++t) {
-                            const float scaled = fabsf(__fdiv_rn(__fsub_rn(x[t], bb.x), den)) * s;
-                            const float cl = fminf(fmaxf(scaled, 0.0f), s - 1.0f);
-                            int li = (int)cl;
-                            if (random) li += (__fsub_rn(scaled, (float)li) > r[t]) ? 1 : 0;
-                            lv[t] = li;
-                        }
-                    }
-                } else {
-                    int sg = seg;
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        const int i = i0 + t;
-                        if (i < n_chunks) {
-                            while (i >= s_seg[sg + 1]) ++sg;
-                            const float2 bb = s_lbub[sg];
-                            lv[t] = psc_level(x[t], bb.x, bb.y, s, random, r[t]);
-                        } else {
-                            lv[t] = 0;
-                        }
-                    }
-                }
-                const uint32_t packed = (uint32_t)lv[0] | ((uint32_t)lv[1] << 8) | ((uint32_t)lv[2] << 16) | ((uint32_t)lv[3] << 24);
-                if (i0 + 3 < n_chunks) {
-                    reinterpret_cast<uint32_t *>(P.l)[q] = packed;
-                } else {
-                    for (int t = 0; t < 4; ++t)
-                        if (i0 + t < n_chunks) P.l[i0 + t] = (uint8_t)lv[t];
-                }
-                if (R.n > 0) {   // the record sections are padded to 256 bytes: whole words may be written remotely
-                    remote_st32(R, reinterpret_cast<uint32_t *>(P.l) + q, packed);
-                    remote_st32(R, reinterpret_cast<uint32_t *>(P.codes) + q, cw[j]);
-                }
-            }
+        finish_pass(q0, xv, rv, cw, seg);
+        for (q0 += J * kThreads; q0 < qe; q0 += J * kThreads) {   // (only when a CTA owns more than 80 tiles)
+            load_pass(q0, xv, rv, cw);
+            finish_pass(q0, xv, rv, cw, seg);
         }
     }
     if (TRACE) __syncthreads();
@@ -853,7 +874,7 @@ struct Variant {
 // fmask | nofmask, f2 | nof2, r2 | r1.  Only the combinations instantiated below exist.
 static Variant pick_variant()
 {
-    Variant v = {3, true, true, true, true};
+    Variant v = {3, true, true, true, false};   // measured best: 3 groups, pair sums, FMA-pipe mask, FFMA2, one group per pass
     if (const char *e = getenv("GQ_TC2")) {
         if (strstr(e, "g4")) v.groups = 4;
         if (strstr(e, "g3")) v.groups = 3;

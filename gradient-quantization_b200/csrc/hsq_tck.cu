@@ -298,15 +298,36 @@ hsq_search_tck_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
                     for (int k0 = 0; k0 < K; k0 += kCoarse) rescore16(k0);
                 }
             } else {
-                for (int t = e; t < T; t += 2) {
+                // Candidate coarse groups of this group's N-tiles as a bit mask first (16 bits per N-tile, two
+                // N-tiles per word), THEN one rescoring pass per set bit: the warp runs max-over-lanes passes
+                // (about three), not one pass per distinct position any of its 32 lanes asks for (about forty).
+                uint32_t cmask[kMaxK / kTileN / 4];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float4 w = s_cm[(t * 4 + q) * kTileM + row];
-                        const int k0 = t * kTileN + q * 64;
-                        if (w.x >= thr) rescore16(k0);
-                        if (w.y >= thr) rescore16(k0 + 16);
-                        if (w.z >= thr) rescore16(k0 + 32);
-                        if (w.w >= thr) rescore16(k0 + 48);
+                for (int w = 0; w < kMaxK / kTileN / 4; ++w) cmask[w] = 0u;
+#pragma unroll
+                for (int tt = 0; tt < kMaxK / kTileN / 2; ++tt) {
+                    const int t = 2 * tt + e;
+                    if (t < T) {
+                        uint32_t bits = 0u;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 w = s_cm[(t * 4 + q) * kTileM + row];
+                            bits |= (w.x >= thr ? 1u : 0u) << (4 * q);
+                            bits |= (w.y >= thr ? 1u : 0u) << (4 * q + 1);
+                            bits |= (w.z >= thr ? 1u : 0u) << (4 * q + 2);
+                            bits |= (w.w >= thr ? 1u : 0u) << (4 * q + 3);
+                        }
+                        cmask[tt >> 1] |= bits << (16 * (tt & 1));
+                    }
+                }
+#pragma unroll
+                for (int w = 0; w < kMaxK / kTileN / 4; ++w) {
+                    uint32_t m = cmask[w];
+                    while (m != 0u) {
+                        const int bit = __ffs((int)m) - 1;
+                        m &= m - 1u;
+                        const int tt = 2 * w + (bit >> 4);
+                        rescore16((2 * tt + e) * kTileN + (bit & 15) * kCoarse);
                     }
                 }
             }
