@@ -95,6 +95,7 @@ struct Enc2 {
     float s;
     int random;
     Remote remote;
+    int wait_hw;                 // bit 0: epilogue, bit 1: MMA warp use the low-latency mbarrier wait
     long long *trace;            // TRACE builds only
 };
 
@@ -174,7 +175,9 @@ __device__ __forceinline__ void issue_tile_mma(uint32_t a_addr, uint32_t b_addr,
 // TRACE builds: CTA 0 time-stamps pipeline events of its first 128 tiles, trace[event * 128 + it] =
 // clock64(): 0 TMA issued, 1 MMA issued, 2 accumulators seen by the epilogue warp, 3 TMEM released
 // (first pass done), 4 smem stage released, 5 candidate mask done, 6 rescoring done, 7 tile done,
-// 8 rescoring iterations of the warp (count, not a time); taken by quadrant 0 / lane 0 of each group.
+// 8 rescoring iterations of the warp (count, not a time); taken by quadrant 0 / lane 0 of each group;
+// 9..11 TMEM released by quadrants 1..3, 12 / 13 MMA warp past its TMEM-empty / smem-full wait,
+// 14 MMA commit seen by a polling observer thread (spare warp 3).
 template <int G, bool PAIR, bool FMASK, bool F2, bool R2 = false, bool TRACE = false>
 __global__ void __launch_bounds__(128 + 128 * G, 1)
 hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_constant__ Enc2 P)
@@ -301,7 +304,7 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
     pdl_wait();
     // TRACE: per-CTA wall-clock stamps (ns) after the trace table: start, main loop done, grid barrier passed, tail done
 #define GQ_STAMP(k) do { if (TRACE && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); \
-        P.trace[9 * 128 + 4 * blockIdx.x + (k)] = (long long)t_; } } while (0)
+        P.trace[16 * 128 + 4 * blockIdx.x + (k)] = (long long)t_; } } while (0)
     GQ_STAMP(0);
 
     if (warp == 0) {
@@ -326,8 +329,15 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
             for (int it = 0; it < my_tiles; ++it) {
                 const int s = it % kStages;
                 const int b = it & 1;
-                if (it >= 2) mbar_wait_sleep(bar_tempty + 8 * ((it - 2) % kStages), ((it - 2) / kStages) & 1);
+                // the operand tile landed long ago (the producer runs kStages ahead): take that wait first,
+                // so that nothing but the issue itself follows the release of the TMEM buffer
                 mbar_wait_sleep(bar_full + 8 * s, (it / kStages) & 1);
+                GQ_TRACE(12, it);
+                if (it >= 2) {
+                    if (P.wait_hw & 2) mbar_wait_hw(bar_tempty + 8 * ((it - 2) % kStages), ((it - 2) / kStages) & 1);
+                    else mbar_wait_sleep(bar_tempty + 8 * ((it - 2) % kStages), ((it - 2) / kStages) & 1);
+                }
+                GQ_TRACE(13, it);
                 tc_fence_after();
                 issue_tile_mma(smem_u32(s_a + s * kTileBytes), smem_u32(s_cb), tmem_base + (uint32_t)(b * kK),
                                bar_tfull + 8 * s);
@@ -348,6 +358,14 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
                 asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(P.flag), "l"(P.id) : "memory");
         }
         rider_run(P.rider, (int64_t)blockIdx.x * 64 + (threadIdx.x - 64), (int64_t)gridDim.x * 64);
+        if (TRACE && blockIdx.x == 0 && warp == 3 && lane == 0) {
+            // observer: polls (no sleep) for the completion of each tile's MMA commit -> event 14
+            for (int it = 0; it < my_tiles && it < 128; ++it) {
+                const int s = it % kStages;
+                while (!mbar_test_wait(bar_tfull + 8 * s, (it / kStages) & 1)) { }
+                GQ_TRACE(14, it);
+            }
+        }
     } else {
         // ----------------------------------------------------------- epilogue ---
         bool keys_ready = P.flag == nullptr;
@@ -376,7 +394,8 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
             const int c = (tile0 + it) * kTileM + row;
             const bool valid = c < n_chunks;
             mbar_wait_sleep(bar_full + 8 * s, ph);    // TMA data visible to this thread
-            mbar_wait_sleep(bar_tfull + 8 * s, ph);   // accumulators complete
+            if (P.wait_hw & 1) mbar_wait_hw(bar_tfull + 8 * s, ph);   // accumulators complete
+            else mbar_wait_sleep(bar_tfull + 8 * s, ph);
             __syncwarp();
             tc_fence_after();
             const bool tracer = TRACE && quad == 0 && lane == 0;
@@ -425,6 +444,7 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * s);
             if (tracer) GQ_TRACE(3, it);
+            if (TRACE && quad != 0 && lane == 0) GQ_TRACE(8 + quad, it);   // 9..11: the other quadrants' releases
 
             // ---- this row's chunk, from the (swizzled) smem tile
             float v[kD];
@@ -920,6 +940,13 @@ static int launch_variant(const Variant &v, const CUtensorMap &mg, const Enc2 &P
     }
 }
 
+// GQ_TC2_WAIT: bit 0 epilogue warps, bit 1 MMA warp wait with plain try_wait (default 3: both)
+static int wait_mode()
+{
+    if (const char *e = getenv("GQ_TC2_WAIT")) return atoi(e) & 3;
+    return 3;
+}
+
 }  // namespace tc2
 
 // default variant with the pipeline trace of CTA 0 (9 x 128 int64) followed by four wall-clock stamps
@@ -956,6 +983,7 @@ int hsq_tc2_trace(const float *grad, int64_t n_chunks, const float *codebook, vo
         P.s = (float)(1u << tail->n_bit);
         P.random = tail->random;
     }
+    P.wait_hw = wait_mode();
     const int n_tiles = (int)((n_chunks + kTileM - 1) / kTileM);
     int sms = sm_count();
     if (const char *g = getenv("GQ_TC_GRID")) {
@@ -1035,6 +1063,7 @@ int hsq_encode_tc2(const float *grad, int64_t n_chunks, const float *codebook, v
             R.epoch = remote->epoch;
         }
     }
+    P.wait_hw = wait_mode();
     const int n_tiles = (int)((n_chunks + kTileM - 1) / kTileM);
     int sms = sm_count();
     if (const char *g = getenv("GQ_TC_GRID")) {

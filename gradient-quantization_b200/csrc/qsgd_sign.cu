@@ -126,6 +126,245 @@ qsgd_quantize_kernel(const float *__restrict__ v, int64_t n, const int64_t *__re
     }
 }
 
+
+// ------------------------------------------------- fast encode, chunked groups ---
+// dim % 4 == 0 and dim <= 2048 (every c_dim the reference is run with: 128 -> 192 -> 288 ...):
+// LPC lanes own one chunk at a time and keep it in registers (NV float4 per lane), so the gradient
+// is read ONCE: chunk L-inf norm by shuffles, then level / sign / packed store from the registers.
+// One launch, no memset, no atomics, no per-element division for the chunk index.
+template <int BITS>
+__device__ __forceinline__ void qsgd_store_packed(void *__restrict__ packed, int64_t q, const uint32_t (&pk)[4])
+{
+    if (BITS == 4) {
+        reinterpret_cast<uint16_t *>(packed)[q] = (uint16_t)(pk[0] | (pk[1] << 4) | (pk[2] << 8) | (pk[3] << 12));
+    } else if (BITS == 8) {
+        reinterpret_cast<uint32_t *>(packed)[q] = pk[0] | (pk[1] << 8) | (pk[2] << 16) | (pk[3] << 24);
+    } else {
+        reinterpret_cast<uint2 *>(packed)[q] = make_uint2(pk[0] | (pk[1] << 16), pk[2] | (pk[3] << 16));
+    }
+}
+
+// four uniforms for elements i0 .. i0 + 3 (i0 % 4 == 0): caller-supplied stream or Philox
+__device__ __forceinline__ void qsgd_uniforms4(int random, const float *__restrict__ uniforms, uint64_t seed,
+                                               uint64_t offset, int64_t i0, float (&r)[4])
+{
+    r[0] = r[1] = r[2] = r[3] = 0.0f;
+    if (!random) return;
+    if (uniforms) {
+        if ((reinterpret_cast<uintptr_t>(uniforms) & 15) == 0) {
+            const float4 t = ld_stream_f4(reinterpret_cast<const float4 *>(uniforms + i0));
+            r[0] = t.x; r[1] = t.y; r[2] = t.z; r[3] = t.w;
+        } else {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) r[t] = uniforms[i0 + t];
+        }
+    } else if (((offset + (uint64_t)i0) & 3u) == 0) {
+        const uint4 w = philox4x32_10(seed, (offset + (uint64_t)i0) >> 2);
+        r[0] = u01(w.x); r[1] = u01(w.y); r[2] = u01(w.z); r[3] = u01(w.w);
+    } else {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) r[t] = philox_uniform(seed, offset, (uint64_t)(i0 + t));
+    }
+}
+
+template <int BITS, int NV, int LPC, int UNR>
+__global__ void __launch_bounds__(256)
+qsgd_encode_chunks_kernel(const float *__restrict__ v, int64_t n_chunks, int dim, float s, int random,
+                          const float *__restrict__ uniforms, uint64_t seed, uint64_t offset,
+                          float *__restrict__ norm, void *__restrict__ packed)
+{
+    pdl_launch_dependents();
+    const int dim4 = dim >> 2;
+    const int sub = threadIdx.x & (LPC - 1);
+    const int64_t n_slots = (int64_t)gridDim.x * (256 / LPC);
+    const int64_t slot = ((int64_t)blockIdx.x * 256 + threadIdx.x) / LPC;
+    const int64_t warp_slot0 = (((int64_t)blockIdx.x * 256 + threadIdx.x) & ~31ll) / LPC;
+    pdl_wait();
+    for (int64_t base = 0; base + warp_slot0 < n_chunks; base += n_slots * UNR) {   // warp-uniform trip count
+        float4 x[UNR][NV];
+        int64_t c[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            c[u] = base + (int64_t)u * n_slots + slot;
+#pragma unroll
+            for (int t = 0; t < NV; ++t) {
+                const int j = sub + t * LPC;
+                x[u][t] = (c[u] < n_chunks && j < dim4)
+                              ? ld_stream_f4(reinterpret_cast<const float4 *>(v) + c[u] * dim4 + j)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            uint32_t a = 0u;
+#pragma unroll
+            for (int t = 0; t < NV; ++t) {
+                a = max(a, __float_as_uint(x[u][t].x) & 0x7fffffffu);
+                a = max(a, __float_as_uint(x[u][t].y) & 0x7fffffffu);
+                a = max(a, __float_as_uint(x[u][t].z) & 0x7fffffffu);
+                a = max(a, __float_as_uint(x[u][t].w) & 0x7fffffffu);
+            }
+#pragma unroll
+            for (int o = LPC / 2; o > 0; o >>= 1) a = max(a, __shfl_xor_sync(0xffffffffu, a, o));
+            const float nm = __uint_as_float(a);
+            if (c[u] >= n_chunks) continue;
+            if (sub == 0) norm[c[u]] = nm;
+#pragma unroll
+            for (int t = 0; t < NV; ++t) {
+                const int j = sub + t * LPC;
+                if (j >= dim4) continue;
+                const int64_t q = c[u] * dim4 + j;
+                float r[4];
+                qsgd_uniforms4(random, uniforms, seed, offset, q * 4, r);
+                const float xe[4] = {x[u][t].x, x[u][t].y, x[u][t].z, x[u][t].w};
+                uint32_t pk[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    bool is_nan;
+                    const int li = qsgd_level(xe[e], nm, s, random, r[e], is_nan);
+                    pk[e] = ((xe[e] > 0.0f ? 1u : 0u) << (BITS - 1)) | (uint32_t)li;
+                }
+                qsgd_store_packed<BITS>(packed, q, pk);
+            }
+        }
+    }
+}
+
+// ------------------------------------- fast encode, explicit chunk boundaries ---
+// TernGrad (one chunk per tensor): every warp walks a CONTIGUOUS range of the group, so the chunk of
+// its elements changes a handful of times: running maximum in registers and one atomicMax per
+// (warp, chunk) in the first kernel, one norm load per chunk change in the second.
+template <int UN>
+__global__ void __launch_bounds__(256)
+seg_absmax_ranges_kernel(const float *__restrict__ v, int64_t n, const int64_t *__restrict__ chunk_start,
+                         int n_chunks, uint32_t *__restrict__ norm_bits)
+{
+    pdl_launch_dependents();
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5, n_warps = (int64_t)gridDim.x * 8;
+    const int64_t span = 128 * UN;
+    const int64_t R = ((n + n_warps - 1) / n_warps + span - 1) / span * span;
+    const int64_t e_begin = warp * R, e_end = min(n, e_begin + R);
+    SegCache sc;
+    int cur = -1;
+    uint32_t cur_max = 0u;
+    pdl_wait();
+    auto flush = [&]() {
+        if (cur >= 0) {
+            const uint32_t w = __reduce_max_sync(0xffffffffu, cur_max);
+            if (lane == 0) atomicMax(norm_bits + cur, w);
+        }
+        cur = -1;
+        cur_max = 0u;
+    };
+    for (int64_t e0 = e_begin; e0 < e_end; e0 += span) {
+        const int64_t e1 = min(e0 + span, e_end);
+        float4 x[UN];
+#pragma unroll
+        for (int t = 0; t < UN; ++t) {
+            const int64_t i0 = e0 + 4 * (lane + 32 * t);
+            if (i0 + 3 < e1) {
+                x[t] = ld_stream_f4(reinterpret_cast<const float4 *>(v + i0));
+            } else {
+                float y[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) y[k] = (i0 + k < e1) ? v[i0 + k] : 0.0f;
+                x[t] = make_float4(y[0], y[1], y[2], y[3]);
+            }
+        }
+        const int first = cached_segment(sc, chunk_start, n_chunks, e0);
+        if (e1 <= sc.hi) {   // the whole span lies in one chunk (warp-uniform)
+            if (first != cur) { flush(); cur = first; }
+#pragma unroll
+            for (int t = 0; t < UN; ++t) {
+                cur_max = max(cur_max, __float_as_uint(x[t].x) & 0x7fffffffu);
+                cur_max = max(cur_max, __float_as_uint(x[t].y) & 0x7fffffffu);
+                cur_max = max(cur_max, __float_as_uint(x[t].z) & 0x7fffffffu);
+                cur_max = max(cur_max, __float_as_uint(x[t].w) & 0x7fffffffu);
+            }
+        } else {             // a chunk boundary inside the span: per element
+            flush();
+#pragma unroll
+            for (int t = 0; t < UN; ++t) {
+                const int64_t i0 = e0 + 4 * (lane + 32 * t);
+                const float y[4] = {x[t].x, x[t].y, x[t].z, x[t].w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (i0 + k < e1)
+                        atomicMax(norm_bits + find_segment(chunk_start, n_chunks, i0 + k),
+                                  __float_as_uint(y[k]) & 0x7fffffffu);
+            }
+        }
+    }
+    flush();
+}
+
+template <int BITS, int UN>
+__global__ void __launch_bounds__(256)
+qsgd_quantize_ranges_kernel(const float *__restrict__ v, int64_t n, const int64_t *__restrict__ chunk_start,
+                            int n_chunks, float s, int random, const float *__restrict__ uniforms,
+                            uint64_t seed, uint64_t offset, const float *__restrict__ norm,
+                            void *__restrict__ packed)
+{
+    pdl_launch_dependents();
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5, n_warps = (int64_t)gridDim.x * 8;
+    const int64_t span = 128 * UN;
+    const int64_t R = ((n + n_warps - 1) / n_warps + span - 1) / span * span;
+    const int64_t e_begin = warp * R, e_end = min(n, e_begin + R);
+    SegCache sc;
+    int cur = -1;
+    float nm_cur = 0.0f;
+    pdl_wait();
+    for (int64_t e0 = e_begin; e0 < e_end; e0 += span) {
+        const int64_t e1 = min(e0 + span, e_end);
+        float4 x[UN];
+#pragma unroll
+        for (int t = 0; t < UN; ++t) {
+            const int64_t i0 = e0 + 4 * (lane + 32 * t);
+            if (i0 + 3 < e1) {
+                x[t] = ld_stream_f4(reinterpret_cast<const float4 *>(v + i0));
+            } else {
+                float y[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) y[k] = (i0 + k < e1) ? v[i0 + k] : 0.0f;
+                x[t] = make_float4(y[0], y[1], y[2], y[3]);
+            }
+        }
+        const int first = cached_segment(sc, chunk_start, n_chunks, e0);
+        const bool uniform = e1 <= sc.hi;
+        if (uniform && first != cur) {
+            cur = first;
+            nm_cur = __ldcg(norm + first);
+        }
+#pragma unroll
+        for (int t = 0; t < UN; ++t) {
+            const int64_t i0 = e0 + 4 * (lane + 32 * t);
+            if (i0 >= e1) continue;
+            float r[4];
+            if (i0 + 3 < n) {
+                qsgd_uniforms4(random, uniforms, seed, offset, i0, r);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    r[k] = (!random || i0 + k >= n) ? 0.0f
+                           : (uniforms ? uniforms[i0 + k] : philox_uniform(seed, offset, (uint64_t)(i0 + k)));
+            }
+            const float y[4] = {x[t].x, x[t].y, x[t].z, x[t].w};
+            uint32_t pk[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (i0 + k >= e1) { pk[k] = 0u; continue; }
+                const float nm = uniform ? nm_cur : __ldcg(norm + find_segment(chunk_start, n_chunks, i0 + k));
+                bool is_nan;
+                const int li = qsgd_level(y[k], nm, s, random, r[k], is_nan);
+                pk[k] = ((y[k] > 0.0f ? 1u : 0u) << (BITS - 1)) | (uint32_t)li;
+            }
+            qsgd_store_packed<BITS>(packed, i0 >> 2, pk);
+        }
+    }
+}
+
 int qsgd_wire_bits(int n_bit) { return n_bit <= 2 ? 4 : (n_bit <= 6 ? 8 : 16); }
 
 int qsgd_encode(const float *grad, int64_t n, const int64_t *chunk_start, int64_t n_chunks, int dim,
@@ -133,11 +372,55 @@ int qsgd_encode(const float *grad, int64_t n, const int64_t *chunk_start, int64_
                 uint8_t *signs, int32_t *l, void *packed, cudaStream_t st)
 {
     if (n == 0) return GQ_OK;
+    const float s = (float)(1u << n_bit);
+    const bool fast_ok = packed && !signs && !l && ((uintptr_t)packed & 15) == 0 && n_chunks < (1ll << 31);
+    if (fast_ok && !chunk_start && dim % 4 == 0 && dim <= 2048) {
+        // one launch: chunk norms and packed levels from registers
+        const int b = qsgd_wire_bits(n_bit);
+        const int dim4 = dim / 4;
+        const int lpc = dim4 <= 8 ? 8 : 32;
+        const int nv = lpc == 8 ? 1 : (dim4 <= 32 ? 1 : dim4 <= 64 ? 2 : dim4 <= 128 ? 4 : dim4 <= 256 ? 8 : 16);
+        const int unr = nv == 1 ? 4 : (nv == 2 ? 2 : 1);
+        const int64_t per_block = (int64_t)(256 / lpc) * unr;
+        const int grid = grid_for(n_chunks, (int)per_block, 16);
+#define GQ_E(B, NV, LPC, UNR) GQ_CUDA(launch_pdl(qsgd_encode_chunks_kernel<B, NV, LPC, UNR>, dim3(grid), dim3(256), 0, st, \
+                                       grad, n_chunks, dim, s, random, uniforms, seed, offset, norm, packed))
+#define GQ_EB(B)                                                  \
+        do {                                                      \
+            if (lpc == 8) GQ_E(B, 1, 8, 4);                       \
+            else if (nv == 1) GQ_E(B, 1, 32, 4);                  \
+            else if (nv == 2) GQ_E(B, 2, 32, 2);                  \
+            else if (nv == 4) GQ_E(B, 4, 32, 1);                  \
+            else if (nv == 8) GQ_E(B, 8, 32, 1);                  \
+            else GQ_E(B, 16, 32, 1);                              \
+        } while (0)
+        if (b == 4) GQ_EB(4);
+        else if (b == 8) GQ_EB(8);
+        else GQ_EB(16);
+#undef GQ_EB
+#undef GQ_E
+        GQ_LAUNCH_CHECK("qsgd_encode_chunks");
+        return GQ_OK;
+    }
     GQ_CUDA(cudaMemsetAsync(norm, 0, (size_t)n_chunks * 4, st));
+    if (fast_ok && chunk_start && ((uintptr_t)grad & 15) == 0) {
+        // explicit chunk boundaries (TernGrad): contiguous range per warp, two launches
+        const int b = qsgd_wire_bits(n_bit);
+        const int grid = grid_for(n, 256 * 4 * 4, 8);
+        GQ_CUDA(launch_pdl(seg_absmax_ranges_kernel<4>, dim3(grid), dim3(256), 0, st, grad, n, chunk_start, (int)n_chunks,
+                           reinterpret_cast<uint32_t *>(norm)));
+#define GQ_R(B) GQ_CUDA(launch_pdl(qsgd_quantize_ranges_kernel<B, 4>, dim3(grid), dim3(256), 0, st, grad, n, chunk_start, \
+                                   (int)n_chunks, s, random, uniforms, seed, offset, (const float *)norm, packed))
+        if (b == 4) GQ_R(4);
+        else if (b == 8) GQ_R(8);
+        else GQ_R(16);
+#undef GQ_R
+        GQ_LAUNCH_CHECK("qsgd_quantize_ranges");
+        return GQ_OK;
+    }
     chunk_absmax_kernel<<<grid_for(n, 256), 256, 0, st>>>(grad, n, chunk_start, n_chunks, dim,
                                                           reinterpret_cast<uint32_t *>(norm));
     GQ_LAUNCH_CHECK("chunk_absmax");
-    const float s = (float)(1u << n_bit);
     const int grid = grid_for((n + 3) / 4, 256);
     const int bits = packed ? qsgd_wire_bits(n_bit) : 0;
 #define GQ_Q(B) qsgd_quantize_kernel<B><<<grid, 256, 0, st>>>(grad, n, chunk_start, n_chunks, dim, s, random, uniforms, seed, offset, norm, signs, l, packed)
@@ -205,14 +488,149 @@ qsgd_decode_reduce_kernel(const float *__restrict__ norm, const void *__restrict
     }
 }
 
+// Fast decode-and-reduce: 8 consecutive elements per thread (one 32 / 64 / 128-bit word of packed
+// levels per user, two float4 stores), the chunk index from one 32-bit division per thread (or the
+// thread's cached segment), "/ s" and a power-of-two "/ U" as exact multiplications by 2^-k.
+template <int BITS, int U_>   // U_ > 0: number of users at compile time
+__global__ void __launch_bounds__(256)
+qsgd_decode_reduce8_kernel(const float *__restrict__ norm, const void *__restrict__ packed, int64_t user_stride,
+                           int n_users_rt, int64_t n, const int64_t *__restrict__ chunk_start, int n_chunks,
+                           uint32_t dim, float inv_s, float inv_u, float div_u, int accumulate,
+                           float *__restrict__ out)
+{
+    pdl_launch_dependents();
+    const int n_users = U_ > 0 ? U_ : n_users_rt;
+    const int64_t n8 = n >> 3;
+    SegCache sc;
+    pdl_wait();
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 255) {
+        // the last n % 8 elements, one by one
+        for (int64_t i = n8 * 8; i < n; ++i) {
+            const int m = chunk_start ? find_segment(chunk_start, n_chunks, i) : (int)((uint64_t)i / dim);
+            float acc = 0.0f;
+            for (int u = 0; u < n_users; ++u) {
+                const uint8_t *pu = reinterpret_cast<const uint8_t *>(packed) + u * user_stride;
+                const float *nu = reinterpret_cast<const float *>(reinterpret_cast<const char *>(norm) + u * user_stride);
+                uint32_t pk;
+                if (BITS == 4) pk = (pu[i >> 1] >> (4 * (i & 1))) & 15u;
+                else if (BITS == 8) pk = pu[i];
+                else pk = reinterpret_cast<const uint16_t *>(pu)[i];
+                const uint32_t sg = pk >> (BITS - 1);
+                const float lf = (float)(int)(pk & ((1u << (BITS - 1)) - 1u));
+                const float val = __fmul_rn(__fmul_rn(__fmul_rn(lf, sg ? 1.0f : -1.0f), nu[m]), inv_s);
+                acc = (u == 0) ? val : __fadd_rn(acc, val);
+            }
+            if (inv_u != 0.0f) acc = __fmul_rn(acc, inv_u);
+            else if (div_u != 0.0f) acc = __fdiv_rn(acc, div_u);
+            if (accumulate) acc = (accumulate == 2) ? __fsub_rn(out[i], acc) : __fadd_rn(out[i], acc);
+            out[i] = acc;
+        }
+    }
+    for (int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x; q < n8; q += (int64_t)gridDim.x * 256) {
+        const int64_t i0 = q * 8;
+        int m[8];
+        bool uni;
+        if (chunk_start) {
+            m[0] = cached_segment(sc, chunk_start, n_chunks, i0);
+            uni = i0 + 7 < sc.hi;
+            if (!uni) {
+#pragma unroll
+                for (int t = 1; t < 8; ++t) m[t] = find_segment(chunk_start, n_chunks, i0 + t);
+            }
+        } else {
+            m[0] = (int)((uint64_t)i0 / dim);
+            uni = (uint32_t)((uint64_t)i0 - (uint64_t)m[0] * dim) + 7u < dim;
+            if (!uni) {
+#pragma unroll
+                for (int t = 1; t < 8; ++t) m[t] = (int)((uint64_t)(i0 + t) / dim);
+            }
+        }
+        float acc[8];
+#pragma unroll
+        for (int u = 0; u < (U_ > 0 ? U_ : 8); ++u) {
+            if (u >= n_users) break;
+            const char *pu = reinterpret_cast<const char *>(packed) + u * user_stride;
+            const float *nu = reinterpret_cast<const float *>(reinterpret_cast<const char *>(norm) + u * user_stride);
+            uint32_t pk[8];
+            if (BITS == 4) {
+                const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(pu) + q);
+#pragma unroll
+                for (int t = 0; t < 8; ++t) pk[t] = (w >> (4 * t)) & 15u;
+            } else if (BITS == 8) {
+                const uint2 w = __ldg(reinterpret_cast<const uint2 *>(pu) + q);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) { pk[t] = (w.x >> (8 * t)) & 255u; pk[4 + t] = (w.y >> (8 * t)) & 255u; }
+            } else {
+                const uint4 w = __ldg(reinterpret_cast<const uint4 *>(pu) + q);
+                pk[0] = w.x & 0xffffu; pk[1] = w.x >> 16; pk[2] = w.y & 0xffffu; pk[3] = w.y >> 16;
+                pk[4] = w.z & 0xffffu; pk[5] = w.z >> 16; pk[6] = w.w & 0xffffu; pk[7] = w.w >> 16;
+            }
+            const float nm0 = __ldg(nu + m[0]);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const float nm = uni ? nm0 : __ldg(nu + m[t]);
+                const uint32_t sg = pk[t] >> (BITS - 1);
+                const float lf = (float)(int)(pk[t] & ((1u << (BITS - 1)) - 1u));
+                // (float(l) * (2 * sign - 1)) * norm / s, qsgd_compressor.py:69-70
+                const float val = __fmul_rn(__fmul_rn(__fmul_rn(lf, sg ? 1.0f : -1.0f), nm), inv_s);
+                acc[t] = (u == 0) ? val : __fadd_rn(acc[t], val);
+            }
+        }
+        float4 o[2];
+        float *of = reinterpret_cast<float *>(o);
+        if (accumulate) {
+            o[0] = reinterpret_cast<const float4 *>(out)[2 * q];
+            o[1] = reinterpret_cast<const float4 *>(out)[2 * q + 1];
+        }
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            float r = acc[t];
+            if (inv_u != 0.0f) r = __fmul_rn(r, inv_u);
+            else if (div_u != 0.0f) r = __fdiv_rn(r, div_u);
+            if (accumulate) r = (accumulate == 2) ? __fsub_rn(of[t], r) : __fadd_rn(of[t], r);
+            of[t] = r;
+        }
+        reinterpret_cast<float4 *>(out)[2 * q] = o[0];
+        reinterpret_cast<float4 *>(out)[2 * q + 1] = o[1];
+    }
+}
+
+// mean over U users: exact multiplication by 1/U when U is a power of two, IEEE division otherwise
+static void mean_factors(int mean, int n_users, float *inv_u, float *div_u)
+{
+    *inv_u = 0.0f;
+    *div_u = 0.0f;
+    if (!mean) return;
+    if ((n_users & (n_users - 1)) == 0) *inv_u = 1.0f / (float)n_users;
+    else *div_u = (float)n_users;
+}
+
 int qsgd_decode_reduce(const float *norm, const void *packed, int64_t user_stride, int n_users,
                        int64_t n, const int64_t *chunk_start, int64_t n_chunks, int dim, int n_bit,
                        int mean, int accumulate, float *out, cudaStream_t st)
 {
     if (n == 0) return GQ_OK;
     const float s = (float)(1u << n_bit);
-    const int grid = grid_for((n + 3) / 4, 256);
     const int bits = qsgd_wire_bits(n_bit);
+    const int64_t n8 = n / 8;
+    if (n_users <= 8 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)packed & 15) == 0 &&
+        (user_stride & 15) == 0 && n < (1ll << 40) && n_chunks < (1ll << 31)) {
+        float inv_u, div_u;
+        mean_factors(mean, n_users, &inv_u, &div_u);
+        const int grid8 = grid_for(n8 + 1, 256, 16);
+#define GQ_D8(B, UU) GQ_CUDA(launch_pdl(qsgd_decode_reduce8_kernel<B, UU>, dim3(grid8), dim3(256), 0, st, norm, packed, user_stride, \
+                                        n_users, n, chunk_start, (int)n_chunks, (uint32_t)(dim > 0 ? dim : 1), 1.0f / s, inv_u, div_u, accumulate, out))
+#define GQ_D8B(B) do { if (n_users == 1) GQ_D8(B, 1); else if (n_users == 2) GQ_D8(B, 2); else if (n_users == 4) GQ_D8(B, 4); \
+                       else if (n_users == 8) GQ_D8(B, 8); else GQ_D8(B, 0); } while (0)
+        if (bits == 4) GQ_D8B(4);
+        else if (bits == 8) GQ_D8B(8);
+        else GQ_D8B(16);
+#undef GQ_D8B
+#undef GQ_D8
+        GQ_LAUNCH_CHECK("qsgd_decode_reduce8");
+        return GQ_OK;
+    }
+    const int grid = grid_for((n + 3) / 4, 256);
 #define GQ_D(B) qsgd_decode_reduce_kernel<B><<<grid, 256, 0, st>>>(norm, packed, user_stride, n_users, n, chunk_start, n_chunks, dim, s, mean, accumulate, out)
     if (bits == 4) GQ_D(4);
     else if (bits == 8) GQ_D(8);
@@ -282,30 +700,68 @@ sign_encode_kernel(const float *__restrict__ v, int64_t n, float *__restrict__ o
     }
 }
 
+// 16 elements per thread: one 32-bit word of packed signs per user, four float4 stores
+template <int U_>
 __global__ void __launch_bounds__(256)
-sign_decode_reduce_kernel(const uint8_t *__restrict__ packed, int64_t user_stride, int n_users,
-                          int64_t n, int mean, int accumulate, float *__restrict__ out)
+sign_decode_reduce_kernel(const uint8_t *__restrict__ packed, int64_t user_stride, int n_users_rt,
+                          int64_t n, float inv_u, float div_u, int accumulate, float *__restrict__ out)
 {
-    const int64_t n4 = (n + 3) / 4;
-    for (int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x; q < n4; q += (int64_t)gridDim.x * 256) {
-        const int64_t i0 = q * 4;
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    pdl_launch_dependents();
+    const int n_users = U_ > 0 ? U_ : n_users_rt;
+    const int64_t n16 = (n + 15) / 16;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(out) & 15) == 0) && ((user_stride & 3) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(packed) & 3) == 0);
+    pdl_wait();
+    for (int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x; q < n16; q += (int64_t)gridDim.x * 256) {
+        const int64_t i0 = q * 16;
+        const bool full = aligned && (i0 + 15 < n);
+        float acc[16];
         for (int u = 0; u < n_users; ++u) {
-            const uint32_t b = packed[u * user_stride + q];
+            const uint8_t *pu = packed + u * user_stride;
+            uint32_t w;
+            if (full) {
+                w = __ldg(reinterpret_cast<const uint32_t *>(pu) + q);
+            } else {
+                w = 0u;
+                for (int k = 0; k < 4; ++k)
+                    if (i0 + 4 * k < n) w |= (uint32_t)pu[q * 4 + k] << (8 * k);
+            }
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const uint32_t c = (b >> (2 * t)) & 3u;
-                const float val = (float)((int)(c & 1u) - (int)(c >> 1));
+            for (int t = 0; t < 16; ++t) {
+                const uint32_t c = (w >> (2 * t)) & 3u;
+                const float val = (c & 1u) ? 1.0f : ((c & 2u) ? -1.0f : 0.0f);
                 acc[t] = (u == 0) ? val : __fadd_rn(acc[t], val);
             }
         }
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            if (i0 + t >= n) continue;
-            float r = acc[t];
-            if (mean) r = __fdiv_rn(r, (float)n_users);
-            if (accumulate) r = (accumulate == 2) ? __fsub_rn(out[i0 + t], r) : __fadd_rn(out[i0 + t], r);
-            out[i0 + t] = r;
+        for (int g = 0; g < 4; ++g) {
+            float r[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                r[t] = acc[4 * g + t];
+                if (inv_u != 0.0f) r[t] = __fmul_rn(r[t], inv_u);
+                else if (div_u != 0.0f) r[t] = __fdiv_rn(r[t], div_u);
+            }
+            const int64_t i = i0 + 4 * g;
+            if (full) {
+                float4 *op = reinterpret_cast<float4 *>(out + i);
+                if (accumulate) {
+                    const float4 o = *op;
+                    r[0] = (accumulate == 2) ? __fsub_rn(o.x, r[0]) : __fadd_rn(o.x, r[0]);
+                    r[1] = (accumulate == 2) ? __fsub_rn(o.y, r[1]) : __fadd_rn(o.y, r[1]);
+                    r[2] = (accumulate == 2) ? __fsub_rn(o.z, r[2]) : __fadd_rn(o.z, r[2]);
+                    r[3] = (accumulate == 2) ? __fsub_rn(o.w, r[3]) : __fadd_rn(o.w, r[3]);
+                }
+                *op = make_float4(r[0], r[1], r[2], r[3]);
+            } else {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    if (i + t >= n) continue;
+                    float x = r[t];
+                    if (accumulate) x = (accumulate == 2) ? __fsub_rn(out[i + t], x) : __fadd_rn(out[i + t], x);
+                    out[i + t] = x;
+                }
+            }
         }
     }
 }
@@ -322,8 +778,17 @@ int sign_decode_reduce(const uint8_t *packed, int64_t user_stride, int n_users, 
                        int accumulate, float *out, cudaStream_t st)
 {
     if (n == 0) return GQ_OK;
-    sign_decode_reduce_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, st>>>(packed, user_stride, n_users, n,
-                                                                          mean, accumulate, out);
+    float inv_u, div_u;
+    mean_factors(mean, n_users, &inv_u, &div_u);
+    const int grid = grid_for((n + 15) / 16, 256, 16);
+#define GQ_S(UU) GQ_CUDA(launch_pdl(sign_decode_reduce_kernel<UU>, dim3(grid), dim3(256), 0, st, packed, user_stride, n_users, n, \
+                                    inv_u, div_u, accumulate, out))
+    if (n_users == 1) GQ_S(1);
+    else if (n_users == 2) GQ_S(2);
+    else if (n_users == 4) GQ_S(4);
+    else if (n_users == 8) GQ_S(8);
+    else GQ_S(0);
+#undef GQ_S
     GQ_LAUNCH_CHECK("sign_decode_reduce");
     return GQ_OK;
 }

@@ -31,6 +31,16 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok;
 }
+__device__ __forceinline__ uint32_t mbar_test_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok;
+}
 // bounded wait: a protocol bug traps (sticky error, process exits) instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, bool backoff = false)
 {
@@ -59,6 +69,24 @@ __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity)
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
         if (t0 == 0ull) t0 = now;
         else if (now - t0 > 4000000000ull) __trap();   // 4 s: a protocol bug, not a slow tile
+    }
+}
+
+// Latency-critical waits (TMEM buffer turnaround): plain try_wait, which blocks in hardware for a
+// short, implementation-defined time and wakes ~60 cycles after the completing arrive -- the
+// suspend-hint form above sleeps through NANOSLEEP.SYNCS and was measured to resume 250-750 cycles
+// after the arrive (tests/tc2_trace.py).  Bounded by wall clock -> trap.
+__device__ __forceinline__ void mbar_wait_hw(uint32_t bar, uint32_t parity)
+{
+    uint32_t spins = 0;
+    unsigned long long t0 = 0ull;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 1023u) == 0u) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0ull) t0 = now;
+            else if (now - t0 > 4000000000ull) __trap();
+        }
     }
 }
 

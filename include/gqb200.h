@@ -252,9 +252,9 @@ int gq_gather_f32(const void *const *src_ptrs, const int64_t *dst_offsets, const
 
 /* Diagnostic hook for the second-generation tcgen05 kernel: search only (l == NULL) or the whole
  * one-launch encode (6-bit norms, Philox), and CTA 0 time-stamps the pipeline events of its first 128
- * tiles into trace (device int64 [9 * 128], clock64 values; event list in hsq_tc2.cu), followed by
+ * tiles into trace (device int64 [16 * 128], clock64 values; event list in hsq_tc2.cu), followed by
  * four wall-clock stamps (ns) per CTA: start, main loop done, grid barrier passed, tail done
- * (trace needs 9 * 128 + 4 * SM-count entries).  How tests/tc2_trace.py measures where the time goes. */
+ * (trace needs 16 * 128 + 4 * SM-count entries).  How tests/tc2_trace.py measures where the time goes. */
 int gq_hsq_tc2_trace(const float *grad, int64_t n_chunks, const float *codebook, void *codes,
                      float *u_out, const int64_t *seg_start, int n_seg, void *l, float *lbub,
                      void *workspace, int64_t *trace, gq_stream_t stream);

@@ -28,7 +28,7 @@ xs = [torch.randn(n * 16, device=dev) * 0.01 for _ in range(3)]
 codes = torch.empty(n, dtype=torch.uint8, device=dev)
 u = torch.empty(n, device=dev)
 GRID = 148
-trace = torch.zeros(9 * 128 + 4 * GRID, dtype=torch.int64, device=dev)
+trace = torch.zeros(16 * 128 + 4 * GRID, dtype=torch.int64, device=dev)
 full = "--encode" in sys.argv
 lv = torch.empty(n, dtype=torch.uint8, device=dev)
 # a ResNet-50-like segment table: 76 tensors of equal size
@@ -41,8 +41,8 @@ for i in range(3):
               lv.data_ptr() if full else None, lbub.data_ptr(), ws.data_ptr(), trace.data_ptr(), _lib.stream())
 torch.cuda.synchronize()
 raw = trace.cpu().numpy().astype(np.int64)
-t = raw[:9 * 128].reshape(9, 128)
-st = raw[9 * 128:].reshape(GRID, 4)
+t = raw[:16 * 128].reshape(16, 128)
+st = raw[16 * 128:].reshape(GRID, 4)
 st = st[st[:, 0] > 0]
 t_first = st[:, 0].min()
 print("per-CTA wall clock (us since the first CTA started), %d CTAs%s:" % (st.shape[0], " [whole encode]" if full else " [search only]"))
@@ -71,3 +71,16 @@ print("  MMA issue -> accumulators seen    : %.0f" % np.mean(ev[2, sl] - ev[1, s
 print("  TMEM release(i) -> MMA issue(i+2) : %.0f" % np.mean(ev[1, lo + 2:hi + 2] - ev[3, lo:hi]))
 print("  TMA issue -> MMA issue            : %.0f" % np.mean(ev[1, sl] - ev[0, sl]))
 print("  total for the CTA: %d cycles for %d tiles" % (ev[7, tiles - 1], tiles))
+
+# round-2 diagnostics: where the TMEM buffer turnaround goes (all four quadrants, MMA warp, polling observer)
+rel_all = np.stack([t[3, :tiles], t[9, :tiles], t[10, :tiles], t[11, :tiles]]) - t0
+last_rel = rel_all.max(axis=0)
+print("  quad release skew (last quad - quad 0)        : %.0f   (last quad - first quad: %.0f)" % (np.mean(last_rel[sl] - ev[3, sl]), np.mean(last_rel[sl] - rel_all.min(axis=0)[sl])))
+m_fu = t[12, :tiles] - t0
+m_te = t[13, :tiles] - t0
+obs = t[14, :tiles] - t0
+print("  last release(i) -> MMA warp past tempty(i+2)  : %.0f" % np.mean(m_te[lo + 2:hi + 2] - last_rel[lo:hi]))
+print("  MMA warp: tempty passed -> issued             : %.0f" % np.mean(ev[1, sl] - m_te[sl]))
+print("  MMA issue -> commit observed by polling warp  : %.0f" % np.mean(obs[sl] - ev[1, sl]))
+print("  commit observed -> epilogue quad 0 sees it    : %.0f" % np.mean(ev[2, sl] - obs[sl]))
+print("  MMA warp idle (prev issue -> tempty passed)   : %.0f" % np.mean(m_te[lo + 1:hi + 1] - ev[1, lo:hi]))
