@@ -118,11 +118,11 @@ int gq_hsq_search(const float *grad, int64_t n_chunks, int d, const float *codeb
     GQ_REQUIRE(n_chunks == 0 || (codes && u_out), "null output pointer");
     GQ_REQUIRE(((uintptr_t)grad & 15) == 0, "gradient must be 16-byte aligned");
     cudaStream_t st = as_stream(stream);
-    const bool tc_ok = hsq_tc_supported(d, K, code_bytes);
+    const bool tc_ok = tc_generation() == 2 ? hsq_tc2_supported(d, K, code_bytes) : hsq_tc_supported(d, K, code_bytes);
     const bool tck_ok = !tc_ok && hsq_tck_supported(d, K, code_bytes) && workspace != nullptr &&
                         ((uintptr_t)workspace & 255) == 0 && workspace_bytes >= hsq_tck_workspace_bytes(d, K);
     if (algo == GQ_ALGO_TC && !tc_ok && !tck_ok) {
-        set_error("tcgen05 search supports d == 16 with K == 256 (uint8 codes) or K = 512..4096, a multiple of 512 "
+        set_error("tcgen05 search supports d in {8, 16, 32} with K == 256 (uint8 codes) or d == 16 with K = 512..4096, a multiple of 512 "
                   "(int32 codes, workspace of gq_hsq_encode_workspace_bytes); got d=%d K=%d code_bytes=%d",
                   d, K, code_bytes);
         return GQ_ERR_UNSUPPORTED;
@@ -135,7 +135,7 @@ int gq_hsq_search(const float *grad, int64_t n_chunks, int d, const float *codeb
             return hsq_search_tc(grad, n_chunks, d, codebook, K, codes, code_bytes, u_out, seg_start, n_seg,
                                  minmax_keys, workspace, workspace_bytes, st);
         // keys (when given) were initialised by the caller: no in-kernel reset, no tail
-        return hsq_encode_tc2(grad, n_chunks, codebook, codes, u_out, seg_start, n_seg, minmax_keys, nullptr, nullptr,
+        return hsq_encode_tc2(grad, n_chunks, d, codebook, codes, u_out, seg_start, n_seg, minmax_keys, nullptr, nullptr,
                               Rider{}, nullptr, nullptr, st);
     }
     return hsq_search_exact(grad, n_chunks, d, codebook, K, codes, code_bytes, u_out, seg_start, n_seg,
@@ -228,7 +228,7 @@ int gq_hsq_encode(const float *grad, int64_t n_chunks, int d, const float *codeb
         return hsq_encode_tc_fused(grad, n_chunks, codebook, codes, u_out, seg_start, n_seg, keys, barrier, n_bit,
                                    random, uniforms, philox_seed, philox_offset, (uint8_t *)l, lbub, st);
     }
-    const bool tc2_ok = tc_generation() == 2 && algo != GQ_ALGO_EXACT && n_chunks > 0 && hsq_tc_supported(d, K, code_bytes);
+    const bool tc2_ok = tc_generation() == 2 && algo != GQ_ALGO_EXACT && n_chunks > 0 && hsq_tc2_supported(d, K, code_bytes);
     if (remote.n > 0 && !(tc2_ok && n_bit != 32 && hsq_tc2_tail_supported(n_seg, n_bit, l_bytes, u_out, uniforms, l, codes))) {
         set_error("a remote delivery is attached, but this encode cannot run as the fused tcgen05 kernel");
         return GQ_ERR_UNSUPPORTED;
@@ -239,16 +239,16 @@ int gq_hsq_encode(const float *grad, int64_t n_chunks, int d, const float *codeb
         GQ_REQUIRE(codes && u_out, "null output pointer");
         uint64_t *flag = reinterpret_cast<uint64_t *>(barrier) + 1;   // barrier word(s) at +0/+4, flag at +8
         if (n_bit == 32) {   // fp32 norms: search only, the rider still travels with it
-            return hsq_encode_tc2(grad, n_chunks, codebook, codes, u_out, seg_start, n_seg, nullptr, nullptr, nullptr,
+            return hsq_encode_tc2(grad, n_chunks, d, codebook, codes, u_out, seg_start, n_seg, nullptr, nullptr, nullptr,
                                   rider, nullptr, nullptr, st);
         }
         GQ_REQUIRE(l && lbub, "null output pointer");
         if (hsq_tc2_tail_supported(n_seg, n_bit, l_bytes, u_out, uniforms, l, codes)) {
             Tc2Tail tail = {(uint8_t *)l, lbub, uniforms, philox_seed, philox_offset, n_bit, random};
-            return hsq_encode_tc2(grad, n_chunks, codebook, codes, u_out, seg_start, n_seg, keys, flag, barrier, rider,
+            return hsq_encode_tc2(grad, n_chunks, d, codebook, codes, u_out, seg_start, n_seg, keys, flag, barrier, rider,
                                   &tail, remote.n > 0 ? &remote : nullptr, st);
         }
-        e = hsq_encode_tc2(grad, n_chunks, codebook, codes, u_out, seg_start, n_seg, keys, flag, nullptr, rider,
+        e = hsq_encode_tc2(grad, n_chunks, d, codebook, codes, u_out, seg_start, n_seg, keys, flag, nullptr, rider,
                            nullptr, nullptr, st);
         if (e) return e;
         return gq_norm_quantize(u_out, n_chunks, seg_start, n_seg, n_bit, random, uniforms, philox_seed,

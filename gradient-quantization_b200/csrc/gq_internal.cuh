@@ -72,7 +72,7 @@ int hsq_search_tck(const float *grad, int64_t n_chunks, const float *codebook, i
 
 int tc_generation();   // abi.cu: 1 = hsq_tc.cu + separate quantize launch, 2 (default) = hsq_tc2.cu
 
-// hsq_tc2.cu: second-generation tcgen05 encode (d == 16, K == 256, uint8 codes).  One launch does the
+// hsq_tc2.cu: second-generation tcgen05 encode (d in {8, 16, 32}, K == 256, uint8 codes).  One launch does the
 // key reset, the identity rider, the search and -- when `tail` is given -- the norm quantization
 // behind a grid barrier; with `remote` it also stores every finished record section into the
 // peers' receive blocks (or once through an NVLS multicast mapping) and announces the step epoch.
@@ -95,7 +95,8 @@ struct Tc2Remote {
 };
 bool hsq_tc2_tail_supported(int n_seg, int n_bit, int l_bytes, const void *u_out, const void *uniforms, const void *l,
                             const void *codes);
-int hsq_encode_tc2(const float *grad, int64_t n_chunks, const float *codebook, void *codes, float *u_out,
+bool hsq_tc2_supported(int d, int K, int code_bytes);   // d in {8, 16, 32}, K == 256, uint8 codes
+int hsq_encode_tc2(const float *grad, int64_t n_chunks, int d, const float *codebook, void *codes, float *u_out,
                    const int64_t *seg_start, int n_seg, uint32_t *keys, uint64_t *flag, uint32_t *barrier,
                    const Rider &rider, const Tc2Tail *tail, const Tc2Remote *remote, cudaStream_t st);
 int hsq_tc2_trace(const float *grad, int64_t n_chunks, const float *codebook, void *codes, float *u_out,

@@ -1,4 +1,4 @@
-// hsq_tc2.cu -- second-generation tcgen05 HSQ encode for d == 16, K == 256 (uint8 codes):
+// hsq_tc2.cu -- second-generation tcgen05 HSQ encode for d in {8, 16, 32}, K == 256 (uint8 codes):
 // ONE launch = min/max key reset + identity rider + TF32 search with exact fp32 rescoring +
 // (after a grid-wide barrier) the n-bit norm quantization of every CTA's own chunk range, and
 // optionally the delivery of the finished record sections into the peers' receive blocks.
@@ -37,29 +37,46 @@ namespace tc2 {
 
 using namespace tcptx;
 
-constexpr int kD = 16;
 constexpr int kK = 256;
 constexpr int kTileM = 128;
-constexpr uint32_t kTileBytes = kTileM * kD * 4;  // 8192
-constexpr uint32_t kCbBytes = kK * kD * 4;        // 16384
 constexpr int kGroup = 4;
 constexpr int kNumGroups = kK / kGroup;           // 64
-constexpr uint32_t kPlanesBytes = 131072;         // rescoring planes (8-fold replicated codebook)
+// Per chunk dimension D: a tile row is one swizzle atom row of the TMA / UMMA layouts (32, 64 or
+// 128 bytes -> SWIZZLE_32B / 64B / 128B), D / 8 tcgen05.mma K-steps per tile.
+template <int D>
+struct Dim {
+    static_assert(D == 8 || D == 16 || D == 32, "chunk dimension");
+    static constexpr uint32_t kRowBytes = D * 4;
+    static constexpr uint32_t kTileBytes = kTileM * kRowBytes;   // 4 / 8 / 16 KB
+    static constexpr uint32_t kCbBytes = kK * kRowBytes;         // TF32 B operand
+    static constexpr int kUnits = D / 4;                         // 16-byte units per row
+    static constexpr uint32_t kPlanesBytes = (D == 8) ? 65536 : 131072;   // rescoring planes (replicated codebook)
+    static constexpr uint64_t kSwizzleCode = (D == 8) ? 6 : (D == 16 ? 4 : 2);   // UMMA layout type
+    // 16-byte unit u of row r is stored at unit u ^ sw(r) (Swizzle<1|2|3, 4, 3>)
+    __device__ static __forceinline__ uint32_t sw(int r)
+    {
+        return D == 8 ? (uint32_t)((r >> 2) & 1) : (D == 16 ? (uint32_t)((r >> 1) & 3) : (uint32_t)(r & 7));
+    }
+};
 constexpr int kTailMaxSeg = 1024;                 // segment tables of the fused tail live in the stage ring
 // 2 * eps / (||v|| * norm scale), see hsq_tc.cu (kMargin) for the derivation; the PAIR variant adds
 // the fp32 rounding of c_a +- c_b (2^-24) and of |p| + |m| (2^-24), covered by the larger slack
 constexpr float kMargin = 2.0f * (1.5f / 1024.0f + 4.0e-6f);
 constexpr float kMarginPair = 2.0f * (1.5f / 1024.0f + 8.0e-6f);
+constexpr float kMarginExtra32 = 2.0f * 4.0e-6f;   // D == 32: twice as many fp32 accumulation steps
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((kK >> 3) << 17) | ((kTileM >> 4) << 24);
 
-template <int G>
+template <int G, int D = 16>
 struct Layout {
-    static constexpr int kStages = (G == 4) ? 8 : 6;   // multiple of 2 (TMEM buffers) and of G
+    // D == 32: four 16 KB stages (64 KB in flight per SM) leave room for four 32 KB rescoring planes
+    static constexpr int kStages = (D == 32) ? 4 : ((G == 4) ? 8 : 6);
     static constexpr uint32_t kOffA = 0;
-    static constexpr uint32_t kOffCb = kStages * kTileBytes;
-    static constexpr uint32_t kOffPlanes = kOffCb + kCbBytes;
-    static constexpr uint32_t kOffBar = kOffPlanes + kPlanesBytes;
+    static constexpr uint32_t kOffCb = kStages * Dim<D>::kTileBytes;
+    static constexpr uint32_t kOffPlanes = kOffCb + Dim<D>::kCbBytes;
+    static constexpr uint32_t kOffBar = kOffPlanes + Dim<D>::kPlanesBytes;
     static constexpr uint32_t kSmemBytes = kOffBar + 512 + 1024;   // + alignment slack
+    static_assert(kSmemBytes <= 232448, "shared memory budget");
+    static_assert(kStages * Dim<D>::kTileBytes >= 4 * (kTailMaxSeg + 2) + 8 * kTailMaxSeg, "tail tables live in the stage ring");
 };
 
 // Where else the finished record sections go (multi-GPU ps exchange fused into the encode):
@@ -163,12 +180,27 @@ __device__ __forceinline__ void remote_st128(const Remote &R, void *local, uint4
     }
 }
 
-// the two K = 8 steps of one 128 x 256 x 16 tile product, then the commit that arrives on `bar`
+// K-major operand descriptor: rows of one swizzle atom (32 / 64 / 128 B), 8-row groups 8 * row bytes apart
+template <int D>
+__device__ __forceinline__ uint64_t make_desc_d(uint32_t saddr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;                                   // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)((8 * Dim<D>::kRowBytes) >> 4) << 32;      // stride byte offset
+    d |= (uint64_t)1 << 46;                                   // descriptor version (Blackwell)
+    d |= Dim<D>::kSwizzleCode << 61;
+    return d;
+}
+
+// the D / 8 K-steps of one 128 x 256 x D tile product, then the commit that arrives on `bar`
+template <int D>
 __device__ __forceinline__ void issue_tile_mma(uint32_t a_addr, uint32_t b_addr, uint32_t taddr, uint32_t bar)
 {
-    const uint64_t adesc = make_desc(a_addr), bdesc = make_desc(b_addr);
-    mma_tf32(taddr, adesc, bdesc, 0u, kIdesc);           // k = 0..7   (bytes  0..31 of each row)
-    mma_tf32(taddr, adesc + 2, bdesc + 2, 1u, kIdesc);   // k = 8..15  (bytes 32..63): +32 B = +2 units
+    const uint64_t adesc = make_desc_d<D>(a_addr), bdesc = make_desc_d<D>(b_addr);
+#pragma unroll
+    for (int ks = 0; ks < D / 8; ++ks)   // k = 8 ks .. 8 ks + 7: bytes 32 ks .. of each row, +32 B = +2 units
+        mma_tf32(taddr, adesc + 2 * ks, bdesc + 2 * ks, ks ? 1u : 0u, kIdesc);
     mma_commit(bar);
 }
 
@@ -178,12 +210,18 @@ __device__ __forceinline__ void issue_tile_mma(uint32_t a_addr, uint32_t b_addr,
 // 8 rescoring iterations of the warp (count, not a time); taken by quadrant 0 / lane 0 of each group;
 // 9..11 TMEM released by quadrants 1..3, 12 / 13 MMA warp past its TMEM-empty / smem-full wait,
 // 14 MMA commit seen by a polling observer thread (spare warp 3).
-template <int G, bool PAIR, bool FMASK, bool F2, bool R2 = false, bool TRACE = false>
+template <int G, bool PAIR, bool FMASK, bool F2, bool R2 = false, bool TRACE = false, int D = 16>
 __global__ void __launch_bounds__(128 + 128 * G, 1)
 hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid_constant__ Enc2 P)
 {
+    static_assert(D != 8 || F2, "d = 8 uses the packed rescoring layout");
+    static_assert(D != 32 || !F2, "d = 32 rescoring is scalar (register budget)");
+    constexpr int kD = D;
+    constexpr uint32_t kTileBytes = Dim<D>::kTileBytes;
+    constexpr uint32_t kRowBytes = Dim<D>::kRowBytes;
+    constexpr int kUnits = Dim<D>::kUnits;
 #define GQ_TRACE(ev, it_) do { if (TRACE && blockIdx.x == 0 && (it_) < 128) P.trace[(ev) * 128 + (it_)] = clock64(); } while (0)
-    using L = Layout<G>;
+    using L = Layout<G, D>;
     constexpr int kThreads = 128 + 128 * G;
     constexpr int kStages = L::kStages;
     pdl_launch_dependents();
@@ -222,7 +260,17 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
     }
     const float *codebook = P.codebook;
     // ---- rescoring planes (exact fp32 codewords, replicated so that lane-divergent LDS.128 never conflict)
-    if constexpr (F2) {
+    if constexpr (F2 && D == 8) {
+        // 4 planes (rotation r) x 128 codeword pairs x 128 bytes; the pair's four 16-byte units
+        // (c_2p[2t], c_2p+1[2t], c_2p[2t+1], c_2p+1[2t+1]) twice (half h) at bank group 4h + ((t + r) & 3)
+        for (int i = threadIdx.x; i < 4 * 128 * 2 * 4; i += kThreads) {
+            const int t = i & 3, h = (i >> 2) & 1, p = (i >> 3) & 127, r = i >> 10;
+            const float2 a = __ldg(reinterpret_cast<const float2 *>(codebook + (2 * p) * kD) + t);
+            const float2 b = __ldg(reinterpret_cast<const float2 *>(codebook + (2 * p + 1) * kD) + t);
+            *reinterpret_cast<float4 *>(s_planes + r * 16384 + p * 128 + 16 * (4 * h + ((t + r) & 3))) =
+                make_float4(a.x, b.x, a.y, b.y);
+        }
+    } else if constexpr (F2) {
         // 8 planes (one per lane class c = lane & 7) x 128 codeword pairs x 128 bytes; 16-byte unit t of
         // pair p = (c_2p[2t], c_2p+1[2t], c_2p[2t+1], c_2p+1[2t+1]) stored at bank group (t + c) & 7
         for (int i = threadIdx.x; i < 8 * 128 * 8; i += kThreads) {
@@ -232,6 +280,14 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
             *reinterpret_cast<float4 *>(s_planes + c * 16384 + p * 128 + 16 * ((t + c) & 7)) =
                 make_float4(a.x, b.x, a.y, b.y);
         }
+    } else if constexpr (D == 32) {
+        // 4 planes (rotation r = lane & 3) x 256 codewords x 128 bytes: unit u at bank group (u + r) & 7
+        // (lanes c and c + 4 of a quarter-warp share a plane: at most two wavefronts per LDS.128)
+        for (int i = threadIdx.x; i < 4 * kK * 8; i += kThreads) {
+            const int u = i & 7, k = (i >> 3) & (kK - 1), r = i >> 11;
+            const float4 val = __ldg(reinterpret_cast<const float4 *>(codebook) + k * 8 + u);
+            *reinterpret_cast<float4 *>(s_planes + r * 32768 + k * 128 + 16 * ((u + r) & 7)) = val;
+        }
     } else {
         // 4 planes (rotation r) x 256 codewords x 128 bytes: unit u twice (half h) at bank group 4h + ((u + r) & 3)
         for (int i = threadIdx.x; i < 4 * kK * 8; i += kThreads) {
@@ -240,25 +296,25 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
             *reinterpret_cast<float4 *>(s_planes + r * 32768 + k * 128 + 16 * (4 * h + ((u + r) & 3))) = val;
         }
     }
-    // ---- MMA B operand, K-major SWIZZLE_64B (row k = 64 bytes, unit u at u ^ ((k >> 1) & 3)), rounded
+    // ---- MMA B operand, K-major swizzled (row k = one atom row, unit u at u ^ sw(k)), rounded
     //      to nearest TF32; PAIR: row 2i = c_2i + c_2i+1, row 2i+1 = c_2i - c_2i+1
-    for (int i = threadIdx.x; i < kK * 4; i += kThreads) {
-        const int u = i & 3, k = i >> 2;
+    for (int i = threadIdx.x; i < kK * kUnits; i += kThreads) {
+        const int u = i % kUnits, k = i / kUnits;
         float4 val;
         if (PAIR) {
-            const float4 a = __ldg(reinterpret_cast<const float4 *>(codebook) + (k & ~1) * 4 + u);
-            const float4 b = __ldg(reinterpret_cast<const float4 *>(codebook) + (k | 1) * 4 + u);
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(codebook) + (k & ~1) * kUnits + u);
+            const float4 b = __ldg(reinterpret_cast<const float4 *>(codebook) + (k | 1) * kUnits + u);
             val = (k & 1) ? make_float4(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y), __fsub_rn(a.z, b.z), __fsub_rn(a.w, b.w))
                           : make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z), __fadd_rn(a.w, b.w));
         } else {
-            val = __ldg(reinterpret_cast<const float4 *>(codebook) + k * 4 + u);
+            val = __ldg(reinterpret_cast<const float4 *>(codebook) + k * kUnits + u);
         }
         uint4 t;
         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t.x) : "f"(val.x));
         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t.y) : "f"(val.y));
         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t.z) : "f"(val.z));
         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t.w) : "f"(val.w));
-        *reinterpret_cast<uint4 *>(s_cb + k * 64 + ((u ^ ((k >> 1) & 3)) << 4)) = t;
+        *reinterpret_cast<uint4 *>(s_cb + k * kRowBytes + ((u ^ Dim<D>::sw(k)) << 4)) = t;
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     // ---- norm scale of the error bound: max ||c_k||, or (PAIR) max over pairs of ||c_a + c_b|| + ||c_a - c_b||
@@ -300,7 +356,7 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
 #pragma unroll
     for (int w = 1; w < kK / 32; ++w) cn = fmaxf(cn, s_cn[w]);
     // (a non-finite codebook gives margin = +inf: threshold -inf / NaN, every group is rescored)
-    const float margin = (PAIR ? kMarginPair : kMargin) * (1.0f + 1.0e-5f) * cn;
+    const float margin = ((PAIR ? kMarginPair : kMargin) + (D == 32 ? kMarginExtra32 : 0.0f)) * (1.0f + 1.0e-5f) * cn;
     pdl_wait();
     // TRACE: per-CTA wall-clock stamps (ns) after the trace table: start, main loop done, grid barrier passed, tail done
 #define GQ_STAMP(k) do { if (TRACE && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); \
@@ -339,8 +395,8 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
                 }
                 GQ_TRACE(13, it);
                 tc_fence_after();
-                issue_tile_mma(smem_u32(s_a + s * kTileBytes), smem_u32(s_cb), tmem_base + (uint32_t)(b * kK),
-                               bar_tfull + 8 * s);
+                issue_tile_mma<D>(smem_u32(s_a + s * kTileBytes), smem_u32(s_cb), tmem_base + (uint32_t)(b * kK),
+                                  bar_tfull + 8 * s);
                 GQ_TRACE(1, it);
             }
         }
@@ -373,12 +429,22 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
         const int quad = warp & 3;
         const int row = quad * 32 + lane;
         uint32_t pbase;
-        uint32_t uo[F2 ? 8 : 4];
-        if constexpr (F2) {
+        uint32_t uo[F2 ? kD / 2 : kUnits];
+        if constexpr (F2 && D == 8) {
+            const int rot = (lane & 7) >> 1, hlf = lane & 1;
+            pbase = smem_u32(s_planes) + rot * 16384 + 64 * hlf;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) uo[t] = 16u * ((t + rot) & 3);
+        } else if constexpr (F2) {
             const int cls = lane & 7;
             pbase = smem_u32(s_planes) + cls * 16384;
 #pragma unroll
             for (int t = 0; t < 8; ++t) uo[t] = 16u * ((t + cls) & 7);
+        } else if constexpr (D == 32) {
+            const int rot = lane & 3;
+            pbase = smem_u32(s_planes) + rot * 32768;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) uo[u] = 16u * ((u + rot) & 7);
         } else {
             const int rot = (lane & 7) >> 1, hlf = lane & 1;
             pbase = smem_u32(s_planes) + rot * 32768 + 64 * hlf;
@@ -449,10 +515,10 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
             // ---- this row's chunk, from the (swizzled) smem tile
             float v[kD];
             {
-                const uint32_t arow = smem_u32(s_a) + s * kTileBytes + row * 64;
-                const int sw = (row >> 1) & 3;
+                const uint32_t arow = smem_u32(s_a) + s * kTileBytes + row * kRowBytes;
+                const uint32_t sw = Dim<D>::sw(row);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < kUnits; ++u) {
                     const float4 t = lds_f4(arow + ((u ^ sw) << 4));
                     v[4 * u] = t.x; v[4 * u + 1] = t.y; v[4 * u + 2] = t.z; v[4 * u + 3] = t.w;
                 }
@@ -538,7 +604,7 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
                     const uint32_t slot = pbase + (uint32_t)g * 256u;   // pair 2g at slot, pair 2g + 1 at slot + 128
                     unsigned long long a01, a23;
 #pragma unroll
-                    for (int t = 0; t < 8; ++t) {
+                    for (int t = 0; t < kD / 2; ++t) {
                         unsigned long long c0, c1, e0, e1;
                         lds_2x64(slot + uo[t], c0, c1);
                         lds_2x64(slot + 128u + uo[t], e0, e1);
@@ -555,20 +621,18 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
                     unpack2(a01, p[0], p[1]);
                     unpack2(a23, p[2], p[3]);
                 } else {
+                    // unit by unit over the four codewords: four independent ascending-j chains
+                    const uint32_t rowa = pbase + (uint32_t)(g * kGroup) * 128u;
 #pragma unroll
-                    for (int i = 0; i < kGroup; ++i) {
-                        const uint32_t rowa = pbase + (uint32_t)(g * kGroup + i) * 128u;
-                        const float4 c0 = lds_f4(rowa + uo[0]);
-                        const float4 c1 = lds_f4(rowa + uo[1]);
-                        const float4 c2 = lds_f4(rowa + uo[2]);
-                        const float4 c3 = lds_f4(rowa + uo[3]);
-                        float acc = __fmul_rn(c0.x, v[0]);
-                        acc = __fmaf_rn(c0.y, v[1], acc);  acc = __fmaf_rn(c0.z, v[2], acc);  acc = __fmaf_rn(c0.w, v[3], acc);
-                        acc = __fmaf_rn(c1.x, v[4], acc);  acc = __fmaf_rn(c1.y, v[5], acc);  acc = __fmaf_rn(c1.z, v[6], acc);
-                        acc = __fmaf_rn(c1.w, v[7], acc);  acc = __fmaf_rn(c2.x, v[8], acc);  acc = __fmaf_rn(c2.y, v[9], acc);
-                        acc = __fmaf_rn(c2.z, v[10], acc); acc = __fmaf_rn(c2.w, v[11], acc); acc = __fmaf_rn(c3.x, v[12], acc);
-                        acc = __fmaf_rn(c3.y, v[13], acc); acc = __fmaf_rn(c3.z, v[14], acc); acc = __fmaf_rn(c3.w, v[15], acc);
-                        p[i] = acc;
+                    for (int u = 0; u < kUnits; ++u) {
+#pragma unroll
+                        for (int i = 0; i < kGroup; ++i) {
+                            const float4 c = lds_f4(rowa + 128u * i + uo[u]);
+                            p[i] = (u == 0) ? __fmul_rn(c.x, v[0]) : __fmaf_rn(c.x, v[4 * u], p[i]);
+                            p[i] = __fmaf_rn(c.y, v[4 * u + 1], p[i]);
+                            p[i] = __fmaf_rn(c.z, v[4 * u + 2], p[i]);
+                            p[i] = __fmaf_rn(c.w, v[4 * u + 3], p[i]);
+                        }
                     }
                 }
             };
@@ -863,7 +927,7 @@ static EncodeTiledFn encode_fn()
     return fn;
 }
 
-static int make_map(CUtensorMap *map, const float *base, int64_t rows)
+static int make_map(CUtensorMap *map, const float *base, int64_t rows, int kD = 16)
 {
     EncodeTiledFn fn = encode_fn();
     if (!fn) {
@@ -875,7 +939,9 @@ static int make_map(CUtensorMap *map, const float *base, int64_t rows)
     cuuint32_t box[2] = {(cuuint32_t)kD, (cuuint32_t)kTileM};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    kD == 8 ? CU_TENSOR_MAP_SWIZZLE_32B : (kD == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B),
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed with CUresult %d (base %p, rows %lld)", (int)r, (const void *)base,
@@ -906,16 +972,16 @@ static Variant pick_variant()
     return v;
 }
 
-template <int G, bool PAIR, bool FMASK, bool F2, bool R2>
+template <int G, bool PAIR, bool FMASK, bool F2, bool R2, int D = 16>
 static int launch_one(const CUtensorMap &mg, const Enc2 &P, int grid, cudaStream_t st)
 {
-    auto kern = hsq_encode_tc2_kernel<G, PAIR, FMASK, F2, R2, false>;
+    auto kern = hsq_encode_tc2_kernel<G, PAIR, FMASK, F2, R2, false, D>;
     static bool attr_set = false;   // per instantiation
     if (!attr_set) {
-        GQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Layout<G>::kSmemBytes));
+        GQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Layout<G, D>::kSmemBytes));
         attr_set = true;
     }
-    GQ_CUDA(launch_pdl(kern, dim3(grid), dim3(128 + 128 * G), (size_t)Layout<G>::kSmemBytes, st, mg, P));
+    GQ_CUDA(launch_pdl(kern, dim3(grid), dim3(128 + 128 * G), (size_t)Layout<G, D>::kSmemBytes, st, mg, P));
     return GQ_OK;
 }
 
@@ -1005,6 +1071,11 @@ int hsq_tc2_trace(const float *grad, int64_t n_chunks, const float *codebook, vo
     return GQ_OK;
 }
 
+bool hsq_tc2_supported(int d, int K, int code_bytes)
+{
+    return (d == 8 || d == 16 || d == 32) && K == tc2::kK && code_bytes == 1;
+}
+
 bool hsq_tc2_tail_supported(int n_seg, int n_bit, int l_bytes, const void *u_out, const void *uniforms, const void *l,
                             const void *codes)
 {
@@ -1014,15 +1085,16 @@ bool hsq_tc2_tail_supported(int n_seg, int n_bit, int l_bytes, const void *u_out
 
 // One-launch encode (or search only when tail == nullptr).  keys == nullptr: no min/max.  flag: 8-byte
 // scratch word for the in-kernel key reset; barrier: 2 x uint32 scratch (grid barrier, delivery counter).
-int hsq_encode_tc2(const float *grad, int64_t n_chunks, const float *codebook, void *codes, float *u_out,
+int hsq_encode_tc2(const float *grad, int64_t n_chunks, int d, const float *codebook, void *codes, float *u_out,
                    const int64_t *seg_start, int n_seg, uint32_t *keys, uint64_t *flag, uint32_t *barrier,
                    const Rider &rider, const Tc2Tail *tail, const Tc2Remote *remote, cudaStream_t st)
 {
     using namespace tc2;
+    GQ_REQUIRE(d == 8 || d == 16 || d == 32, "tcgen05 encode: chunk dimension %d (8, 16 or 32)", d);
     GQ_REQUIRE(((uintptr_t)grad & 15) == 0 && ((uintptr_t)codebook & 15) == 0, "TMA needs 16-byte aligned bases");
     GQ_REQUIRE(n_chunks > 0 && n_chunks < ((int64_t)1 << 31) - 256, "n_chunks out of range for one tensor map");
     CUtensorMap mg;
-    int e = make_map(&mg, grad, n_chunks);
+    int e = make_map(&mg, grad, n_chunks, d);
     if (e) return e;
     static std::atomic<unsigned long long> counter{[] {
         unsigned long long seed = (unsigned long long)(uintptr_t)&seed ^ (unsigned long long)clock();
@@ -1071,8 +1143,14 @@ int hsq_encode_tc2(const float *grad, int64_t n_chunks, const float *codebook, v
         if (v > 0 && v < sms) sms = v;
     }
     const int grid = n_tiles < sms ? n_tiles : sms;
-    const Variant v = pick_variant();
-    e = launch_variant(v, mg, P, grid, st);
+    if (d == 8) {          // one variant each for the other chunk dimensions (the measured-best switches)
+        e = launch_one<3, true, true, true, false, 8>(mg, P, grid, st);
+    } else if (d == 32) {
+        e = launch_one<3, true, true, false, false, 32>(mg, P, grid, st);
+    } else {
+        const Variant v = pick_variant();
+        e = launch_variant(v, mg, P, grid, st);
+    }
     if (e) return e;
     GQ_LAUNCH_CHECK("hsq_encode_tc2");
     return GQ_OK;

@@ -89,6 +89,18 @@ __device__ __forceinline__ float exact_score(const float *__restrict__ codebook,
     return acc;
 }
 
+// max |x| over 16 accumulators as a depth-3 tree of 3-input maxima (a serial chain of eight
+// dependent FMNMX3 made the first pass latency-bound: one warp per scheduler and group)
+__device__ __forceinline__ float absmax16(const uint32_t (&s)[16])
+{
+    auto a = [&](int i) { return fabsf(__uint_as_float(s[i])); };
+    const float m0 = fmaxf(fmaxf(a(0), a(1)), a(2)), m1 = fmaxf(fmaxf(a(3), a(4)), a(5));
+    const float m2 = fmaxf(fmaxf(a(6), a(7)), a(8)), m3 = fmaxf(fmaxf(a(9), a(10)), a(11));
+    const float m4 = fmaxf(fmaxf(a(12), a(13)), a(14));
+    const float n0 = fmaxf(fmaxf(m0, m1), m2), n1 = fmaxf(fmaxf(m3, m4), a(15));
+    return fmaxf(n0, n1);
+}
+
 __device__ __forceinline__ void named_barrier(int id, int threads)
 {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
@@ -214,22 +226,10 @@ hsq_search_tck_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
 #pragma unroll
                 for (int h = 0; h < 8; ++h) {
                     tmem_ld16(taddr + h * 32 + 16, sb);
-                    {
-                        float m = fmaxf(fabsf(__uint_as_float(sa[0])), fabsf(__uint_as_float(sa[1])));
-#pragma unroll
-                        for (int i = 2; i < 16; i += 2)
-                            m = fmaxf(fmaxf(m, fabsf(__uint_as_float(sa[i]))), fabsf(__uint_as_float(sa[i + 1])));
-                        cm[2 * h] = m;
-                    }
+                    cm[2 * h] = absmax16(sa);
                     tmem_ld_wait16(sb);
                     if (h + 1 < 8) tmem_ld16(taddr + h * 32 + 32, sa);
-                    {
-                        float m = fmaxf(fabsf(__uint_as_float(sb[0])), fabsf(__uint_as_float(sb[1])));
-#pragma unroll
-                        for (int i = 2; i < 16; i += 2)
-                            m = fmaxf(fmaxf(m, fabsf(__uint_as_float(sb[i]))), fabsf(__uint_as_float(sb[i + 1])));
-                        cm[2 * h + 1] = m;
-                    }
+                    cm[2 * h + 1] = absmax16(sb);
                     if (h + 1 < 8) tmem_ld_wait16(sa);
                 }
                 // release the TMEM buffer; the last of the group's four warps issues the MMA of pair j + 2

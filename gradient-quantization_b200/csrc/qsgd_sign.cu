@@ -231,20 +231,21 @@ qsgd_encode_chunks_kernel(const float *__restrict__ v, int64_t n_chunks, int dim
 }
 
 // ------------------------------------- fast encode, explicit chunk boundaries ---
-// TernGrad (one chunk per tensor): every warp walks a CONTIGUOUS range of the group, so the chunk of
-// its elements changes a handful of times: running maximum in registers and one atomicMax per
-// (warp, chunk) in the first kernel, one norm load per chunk change in the second.
+// TernGrad (one chunk per tensor): every warp walks increasing addresses of one CTA-owned range, so
+// the chunk of its elements changes a handful of times: running maximum in registers and one
+// atomicMax per (warp, chunk) in the first kernel, one norm load per chunk change in the second.
 template <int UN>
 __global__ void __launch_bounds__(256)
 seg_absmax_ranges_kernel(const float *__restrict__ v, int64_t n, const int64_t *__restrict__ chunk_start,
                          int n_chunks, uint32_t *__restrict__ norm_bits)
 {
     pdl_launch_dependents();
+    // every CTA owns a contiguous range, its eight warps take the spans of that range in turn (the
+    // CTA streams 8 consecutive spans at a time; a warp still sees increasing addresses)
     const int lane = threadIdx.x & 31;
-    const int64_t warp = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5, n_warps = (int64_t)gridDim.x * 8;
     const int64_t span = 128 * UN;
-    const int64_t R = ((n + n_warps - 1) / n_warps + span - 1) / span * span;
-    const int64_t e_begin = warp * R, e_end = min(n, e_begin + R);
+    const int64_t R = ((n + gridDim.x - 1) / gridDim.x + 8 * span - 1) / (8 * span) * (8 * span);
+    const int64_t e_begin = (int64_t)blockIdx.x * R + (threadIdx.x >> 5) * span, e_end = min(n, (int64_t)(blockIdx.x + 1) * R);
     SegCache sc;
     int cur = -1;
     uint32_t cur_max = 0u;
@@ -257,7 +258,7 @@ seg_absmax_ranges_kernel(const float *__restrict__ v, int64_t n, const int64_t *
         cur = -1;
         cur_max = 0u;
     };
-    for (int64_t e0 = e_begin; e0 < e_end; e0 += span) {
+    for (int64_t e0 = e_begin; e0 < e_end; e0 += 8 * span) {
         const int64_t e1 = min(e0 + span, e_end);
         float4 x[UN];
 #pragma unroll
@@ -307,16 +308,17 @@ qsgd_quantize_ranges_kernel(const float *__restrict__ v, int64_t n, const int64_
                             void *__restrict__ packed)
 {
     pdl_launch_dependents();
+    // every CTA owns a contiguous range, its eight warps take the spans of that range in turn (the
+    // CTA streams 8 consecutive spans at a time; a warp still sees increasing addresses)
     const int lane = threadIdx.x & 31;
-    const int64_t warp = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5, n_warps = (int64_t)gridDim.x * 8;
     const int64_t span = 128 * UN;
-    const int64_t R = ((n + n_warps - 1) / n_warps + span - 1) / span * span;
-    const int64_t e_begin = warp * R, e_end = min(n, e_begin + R);
+    const int64_t R = ((n + gridDim.x - 1) / gridDim.x + 8 * span - 1) / (8 * span) * (8 * span);
+    const int64_t e_begin = (int64_t)blockIdx.x * R + (threadIdx.x >> 5) * span, e_end = min(n, (int64_t)(blockIdx.x + 1) * R);
     SegCache sc;
     int cur = -1;
     float nm_cur = 0.0f;
     pdl_wait();
-    for (int64_t e0 = e_begin; e0 < e_end; e0 += span) {
+    for (int64_t e0 = e_begin; e0 < e_end; e0 += 8 * span) {
         const int64_t e1 = min(e0 + span, e_end);
         float4 x[UN];
 #pragma unroll

@@ -297,7 +297,7 @@ class FusedPlan:
         rng_user: logical user whose Philox stream the stochastic rounding draws from (default: the
         record row); shared_rng: the rank-independent stream instead (second phase of --two-phase).
         Launches: HSQ 2 per group on the tcgen05 path (search, quantize; 3 with the separate init
-        kernel of the exact path), QSGD 3, sign 1, top-k 12; the copy of the identity tensors rides
+        kernel of the exact path), QSGD 1 (chunked) or 3, sign 1, top-k 10; the copy of the identity tensors rides
         in the first HSQ group's first kernel (1 launch of its own when there is no HSQ group)."""
         src = self.arena if src is None else src
         src_ptr = src if isinstance(src, int) else src.data_ptr()   # tensor or raw device address
@@ -372,7 +372,7 @@ class FusedPlan:
         if len(hsq) != 1 or hsq[0].kind != "hsq":
             return False
         g = hsq[0]
-        return (g.dim == 16 and g.K == 256 and g.code_bytes == 1 and g.n_bit <= 7 and g.l_bytes == 1
+        return (g.dim in (8, 16, 32) and g.K == 256 and g.code_bytes == 1 and g.n_bit <= 7 and g.l_bytes == 1
                 and g.n_seg <= 1024 and g.n_chunks > 0)
 
     def supports_inplace_feedback(self):
@@ -437,13 +437,13 @@ class FusedPlan:
         return out
 
     def launches_per_encode(self):
-        per = {"hsq": 3, "qsgd": 3, "sign": 1, "topk": 12, "identity": 1}
+        per = {"hsq": 3, "qsgd": 3, "sign": 1, "topk": 10, "identity": 1}
         n = 0
         for g in self.groups:
             k = per[g.kind]
             if g.kind == "hsq" and g.n_bit == 32:
                 k -= 2          # search only
-            elif (g.kind == "hsq" and g.dim == 16 and g.K == 256 and g.code_bytes == 1
+            elif (g.kind == "hsq" and g.dim in (8, 16, 32) and g.K == 256 and g.code_bytes == 1
                   and self.algo != _lib.ALGO_EXACT):
                 # tcgen05: the search kernel resets the min/max keys itself; second generation: the norm
                 # quantization is its fused tail as well (one launch)
