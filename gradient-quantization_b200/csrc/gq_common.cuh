@@ -85,6 +85,7 @@ __host__ __device__ __forceinline__ float key_to_float(uint32_t k)
 }
 #define GQ_KEY_MIN_INIT 0xffffffffu
 #define GQ_KEY_MAX_INIT 0x00000000u
+#define GQ_KEY_NAN 0xffc00000u      // key of +NaN: above +inf, so a NaN input reaches ub (and the decoded tensor)
 
 // ---------------------------------------------------------------- philox ---
 // Philox4x32-10, counter = (idx_lo, idx_hi, 0, 0), key = seed.  One call gives

@@ -176,6 +176,7 @@ __device__ __forceinline__ void search_epilogue(bool valid, int64_t c, int best_
     // warp-uniform fast path: every valid lane in the same tensor
     int seg0 = __shfl_sync(0xffffffffu, seg, 0);
     bool uniform = __all_sync(0xffffffffu, (seg == seg0) || !valid) && (seg0 >= 0);
+    if (valid && best_u != best_u) atomicMax(minmax_keys + 2 * seg + 1, GQ_KEY_NAN);   // NaN propagates (see minmax_add_warp)
     if (uniform) {
         float mn = warp_min(valid ? best_u : INFINITY);
         float mx = warp_max(valid ? best_u : -INFINITY);
@@ -304,6 +305,9 @@ __device__ __forceinline__ void minmax_add_warp(MinMaxAcc &a, bool valid, int se
                                                 uint32_t *__restrict__ keys)
 {
     if (__any_sync(0xffffffffu, valid && a.seg >= 0 && seg != a.seg)) minmax_flush_warp(a, keys);
+    // fminf / fmaxf drop NaN; the reference's torch.min / torch.max propagate it (the whole tensor then
+    // decodes to NaN): a NaN score goes straight into the max key, which orders above +inf
+    if (valid && u != u) atomicMax(keys + 2 * seg + 1, GQ_KEY_NAN);
     if (valid) {
         a.seg = seg;
         a.mn = fminf(a.mn, u);

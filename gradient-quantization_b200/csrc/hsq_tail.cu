@@ -26,6 +26,8 @@ seg_minmax_kernel(const float *__restrict__ u, int64_t n, const int64_t *__restr
         int seg = valid ? cached_segment(segc, seg_start, n_seg, i) : -1;
         int seg0 = __shfl_sync(0xffffffffu, seg, 0);
         bool uniform = __all_sync(0xffffffffu, (seg == seg0) || !valid) && (seg0 >= 0);
+        // torch.min / torch.max propagate NaN (fminf / fmaxf drop it): it goes into the max key, above +inf
+        if (valid && x != x) atomicMax(keys + 2 * seg + 1, GQ_KEY_NAN);
         if (uniform) {
             float mn = warp_min(valid ? x : INFINITY);
             float mx = warp_max(valid ? x : -INFINITY);

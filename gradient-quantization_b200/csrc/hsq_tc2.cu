@@ -74,7 +74,7 @@ struct Layout {
     static constexpr uint32_t kOffCb = kStages * Dim<D>::kTileBytes;
     static constexpr uint32_t kOffPlanes = kOffCb + Dim<D>::kCbBytes;
     static constexpr uint32_t kOffBar = kOffPlanes + Dim<D>::kPlanesBytes;
-    static constexpr uint32_t kSmemBytes = kOffBar + 512 + 1024;   // + alignment slack
+    static constexpr uint32_t kSmemBytes = kOffBar + 1024 + 1024;   // barriers + code staging, + alignment slack
     static_assert(kSmemBytes <= 232448, "shared memory budget");
     static_assert(kStages * Dim<D>::kTileBytes >= 4 * (kTailMaxSeg + 2) + 8 * kTailMaxSeg, "tail tables live in the stage ring");
 };
@@ -239,6 +239,8 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
     float *s_cn = reinterpret_cast<float *>(smem + L::kOffBar + 8 * (4 * kStages) + 8);   // [8] per-warp norm maxima
     int *s_misc = reinterpret_cast<int *>(smem + L::kOffBar + 8 * (4 * kStages) + 8 + 32);
     static_assert(8 * (4 * kStages) + 8 + 32 + 16 <= 512, "barrier region");
+    uint8_t *s_codes = smem + L::kOffBar + 512;   // [4 * G warps][32] codes of a warp-tile, staged for 16-byte stores
+    static_assert(4 * G * 32 <= 512, "code staging");
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -453,6 +455,7 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
         }
         SegCache segc;
         MinMaxAcc mm;
+        const bool codes16 = (reinterpret_cast<uintptr_t>(P.codes) & 15) == 0;
         for (int it = egroup; it < my_tiles; it += G) {
             const int s = it % kStages;
             const uint32_t ph = (it / kStages) & 1;
@@ -554,12 +557,17 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
                 const float thrm = __uint_as_float(tb - 1u);
                 const float S = __uint_as_float(0x8B000000u - (tb & 0x7F800000u));
                 const float T = -__fmul_rn(thrm, S);
-                float mk[4] = {1.0f, 1.0f, 1.0f, 1.0f};
+                // (the shift-accumulate step runs two chains per instruction: packed fma.rn.f32x2)
+                const unsigned long long two2 = pack2(2.0f, 2.0f);
+                unsigned long long mk01 = pack2(1.0f, 1.0f), mk23 = mk01;
 #pragma unroll
                 for (int g = 15; g >= 0; --g) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) mk[q] = __fmaf_rn(mk[q], 2.0f, fma_sat(gm[16 * q + g], S, T));
+                    mk01 = ffma2(mk01, two2, pack2(fma_sat(gm[g], S, T), fma_sat(gm[16 + g], S, T)));
+                    mk23 = ffma2(mk23, two2, pack2(fma_sat(gm[32 + g], S, T), fma_sat(gm[48 + g], S, T)));
                 }
+                float mk[4];
+                unpack2(mk01, mk[0], mk[1]);
+                unpack2(mk23, mk[2], mk[3]);
                 clo = ((__float_as_uint(mk[0]) >> 7) & 0xffffu) | ((__float_as_uint(mk[1]) << 9) & 0xffff0000u);
                 chi = ((__float_as_uint(mk[2]) >> 7) & 0xffffu) | ((__float_as_uint(mk[3]) << 9) & 0xffff0000u);
             } else {
@@ -688,9 +696,26 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
                     if (blockIdx.x == 0 && it < 128) P.trace[8 * 128 + it] = n_iter;
                 }
             }
-            if (valid) {
+            if (valid) P.u_out[c] = best_u;
+            if (codes16) {
+                // the warp's 32 codes leave as two 16-byte stores (and, multi-GPU, go to the peers' receive
+                // blocks from here: that half of the record crosses NVLink while the search is still running)
+                uint8_t *slot = s_codes + (warp - 4) * 32;
+                slot[lane] = valid ? (uint8_t)best_k : (uint8_t)0;
+                __syncwarp();
+                if ((lane & 15) == 0) {
+                    const uint4 w = *reinterpret_cast<const uint4 *>(slot + lane);
+                    if (c + 15 < n_chunks) {
+                        *reinterpret_cast<uint4 *>(P.codes + c) = w;
+                    } else {
+                        for (int t = 0; t < 16; ++t)
+                            if (c + t < n_chunks) P.codes[c + t] = slot[lane + t];
+                    }
+                    if (P.remote.n > 0 && c < n_chunks) remote_st128(P.remote, P.codes + c, w);
+                }
+                __syncwarp();
+            } else if (valid) {
                 P.codes[c] = (uint8_t)best_k;
-                P.u_out[c] = best_u;
             }
             if (P.keys != nullptr) {
                 if (!keys_ready) {   // CTA 0 has reset the keys; bounded wait, then trap
@@ -745,25 +770,22 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
     const bool philox_aligned = (P.offset & 3u) == 0;
     constexpr int J = 5;   // float4 groups per thread and pass: 512 threads x 5 x 4 = 10240 chunks >= 78 tiles
     // u (and codes / uniforms / Philox draws) of up to J groups of four chunks, q0, q0 + kThreads, ...
-    auto load_pass = [&](int q0, float4 (&xv)[J], float4 (&rv)[J], uint32_t (&cw)[J]) {
+    auto load_pass = [&](int q0, float4 (&xv)[J], float4 (&rv)[J]) {
 #pragma unroll
         for (int j = 0; j < J; ++j) {
             const int q = q0 + j * kThreads;
             xv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
             rv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            cw[j] = 0u;
             if (q < qe) {
                 if (q * 4 + 3 < n_chunks) {
                     xv[j] = __ldcg(reinterpret_cast<const float4 *>(P.u_out) + q);
                     if (ext) rv[j] = __ldg(reinterpret_cast<const float4 *>(P.uniforms) + q);
-                    if (R.n > 0) cw[j] = __ldcg(reinterpret_cast<const uint32_t *>(P.codes) + q);
                 } else {
                     float x[4] = {0.f, 0.f, 0.f, 0.f}, r[4] = {0.f, 0.f, 0.f, 0.f};
                     for (int t = 0; t < 4; ++t) {
                         if (q * 4 + t < n_chunks) {
                             x[t] = __ldcg(P.u_out + q * 4 + t);
                             if (ext) r[t] = __ldg(P.uniforms + q * 4 + t);
-                            if (R.n > 0) cw[j] |= (uint32_t)__ldcg(P.codes + q * 4 + t) << (8 * t);
                         }
                     }
                     xv[j] = make_float4(x[0], x[1], x[2], x[3]);
@@ -787,12 +809,15 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
             }
         }
     };
-    // levels of those groups (needs lb/ub: after the barrier), stored locally and at the remote copies
-    auto finish_pass = [&](int q0, const float4 (&xv)[J], const float4 (&rv)[J], const uint32_t (&cw)[J], int &seg) {
+    // levels of those groups (needs lb/ub: after the barrier), stored locally and -- four lanes' words
+    // gathered into one 16-byte store -- at the remote copies (the codes went out from the main loop)
+    auto finish_pass = [&](int q0, const float4 (&xv)[J], const float4 (&rv)[J], int &seg) {
 #pragma unroll
         for (int j = 0; j < J; ++j) {
             const int q = q0 + j * kThreads;
-            if (q >= qe) continue;
+            const bool act = q < qe;
+            uint32_t packed = 0u;
+            if (act) {
             const int i0 = q * 4;
             const float x[4] = {xv[j].x, xv[j].y, xv[j].z, xv[j].w};
             const float r[4] = {rv[j].x, rv[j].y, rv[j].z, rv[j].w};
@@ -827,23 +852,25 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
                     }
                 }
             }
-            const uint32_t packed = (uint32_t)lv[0] | ((uint32_t)lv[1] << 8) | ((uint32_t)lv[2] << 16) | ((uint32_t)lv[3] << 24);
+            packed = (uint32_t)lv[0] | ((uint32_t)lv[1] << 8) | ((uint32_t)lv[2] << 16) | ((uint32_t)lv[3] << 24);
             if (i0 + 3 < n_chunks) {
                 reinterpret_cast<uint32_t *>(P.l)[q] = packed;
             } else {
                 for (int t = 0; t < 4; ++t)
                     if (i0 + t < n_chunks) P.l[i0 + t] = (uint8_t)lv[t];
             }
-            if (R.n > 0) {   // the record sections are padded to 256 bytes: whole words may be written remotely
-                remote_st32(R, reinterpret_cast<uint32_t *>(P.l) + q, packed);
-                remote_st32(R, reinterpret_cast<uint32_t *>(P.codes) + q, cw[j]);
+            }
+            if (R.n > 0) {   // the record sections are padded to 256 bytes: whole 16-byte words may be written remotely
+                const uint32_t p1 = __shfl_down_sync(0xffffffffu, packed, 1), p2 = __shfl_down_sync(0xffffffffu, packed, 2);
+                const uint32_t p3 = __shfl_down_sync(0xffffffffu, packed, 3);
+                if (act && (threadIdx.x & 3) == 0)
+                    remote_st128(R, reinterpret_cast<uint32_t *>(P.l) + q, make_uint4(packed, p1, p2, p3));
             }
         }
     };
     float4 xv[J], rv[J];
-    uint32_t cw[J];
     int q0 = qb + (int)threadIdx.x;
-    load_pass(q0, xv, rv, cw);
+    load_pass(q0, xv, rv);
     if (threadIdx.x == 0) {
         uint32_t seen, spins = 0;
         do {
@@ -878,10 +905,10 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
             }
             seg = lo;
         }
-        finish_pass(q0, xv, rv, cw, seg);
-        for (q0 += J * kThreads; q0 < qe; q0 += J * kThreads) {   // (only when a CTA owns more than 80 tiles)
-            load_pass(q0, xv, rv, cw);
-            finish_pass(q0, xv, rv, cw, seg);
+        finish_pass(q0, xv, rv, seg);
+        for (q0 += J * kThreads; q0 - (int)threadIdx.x < qe; q0 += J * kThreads) {   // (only when a CTA owns more than 80 tiles)
+            load_pass(q0, xv, rv);
+            finish_pass(q0, xv, rv, seg);
         }
     }
     if (TRACE) __syncthreads();
@@ -1123,6 +1150,8 @@ int hsq_encode_tc2(const float *grad, int64_t n_chunks, int d, const float *code
         P.s = (float)(1u << tail->n_bit);
         P.random = tail->random;
         if (remote != nullptr && remote->n > 0) {
+            GQ_REQUIRE(((uintptr_t)codes & 15) == 0 && ((uintptr_t)tail->l & 15) == 0,
+                       "remote delivery needs 16-byte aligned codes / l sections");
             Remote &R = P.remote;
             R.n = remote->n;
             R.multicast = remote->multicast;

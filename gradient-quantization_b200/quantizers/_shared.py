@@ -45,8 +45,12 @@ class QuantizerBase(object):
                                % (args.num_users, self.world))
         use_fused = getattr(args, "fused", True) and FusedPlan.supports(Compressor)
         if use_fused and Compressor.__name__ == "NearestNeighborCompressor":
-            # K == dim asks for a per-tensor random orthogonal basis: per-parameter path only
-            use_fused = not (args.k_bit <= 0)
+            # K == dim asks for a per-tensor random orthogonal basis (nearest_neighbor_compressor.py:45):
+            # per-parameter path only.  That is k_bit <= 0, or 2 ** k_bit equal to the (possibly
+            # escalated) chunk dimension of any compressed tensor, e.g. c_dim = 16 with k_bit = 4.
+            from ..compressors._common import chunk_dim
+            sizes = [int(p.numel()) for p in self.parameters if int(p.numel()) > 1000]
+            use_fused = args.k_bit > 0 and all(chunk_dim(n, args.c_dim) != 2 ** args.k_bit for n in sizes)
         if self.distributed and not use_fused:
             raise _lib.GQError("distributed exchange needs a compressor with a packed wire format")
         self.plan = None

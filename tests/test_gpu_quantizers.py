@@ -138,3 +138,39 @@ def test_identity_tensors_follow_every_hsq_path(c_dim, n_bit, users):
             assert np.array_equal(got, r_)
         else:
             assert np.abs(got - r_).max() <= 1e-6 * max(np.abs(r_).max(), 1e-30)
+
+
+def test_codebook_size_equal_to_chunk_dim_takes_the_per_parameter_path():
+    """2 ** k_bit == chunk dim (c_dim 16, k_bit 4) asks for random orthogonal bases
+    (nearest_neighbor_compressor.py:45): the quantizer must fall back to per-parameter compressors
+    instead of failing in the fused plan (round-1 advisor finding)."""
+    shapes = [(64, 128), (100,)]
+    a = make_args(num_users=2, c_dim=16, k_bit=4, random=False)
+    params = [torch.nn.Parameter(torch.zeros(s, device=DEV)) for s in shapes]
+    q = gq_b200.Quantizer(gq_b200.NearestNeighborCompressor, params, a)
+    assert q.plan is None
+    for u in range(2):
+        for i, (p, s) in enumerate(zip(params, shapes)):
+            p.grad = torch.from_numpy(gen_input(u * 10 + i, int(np.prod(s)))).view(s).to(DEV)
+        q.record(u, epoch=0)
+    q.apply()
+    assert all(torch.isfinite(p.grad).all() for p in params)
+
+
+@pytest.mark.parametrize("algo", ["auto", "exact"])
+def test_nan_gradient_makes_the_whole_tensor_nan(algo):
+    """torch.min / torch.max propagate NaN in the reference (probabilistic_scalar_compressor.py:14-15):
+    one NaN element turns the decoded tensor into NaN; the other tensors are untouched."""
+    from gq_b200 import _lib
+    shapes = [(64, 128), (32, 64)]
+    a = make_args(num_users=1, random=False, hsq_algo={"auto": _lib.ALGO_AUTO, "exact": _lib.ALGO_EXACT}[algo])
+    params = [torch.nn.Parameter(torch.zeros(s, device=DEV)) for s in shapes]
+    q = gq_b200.Quantizer(gq_b200.NearestNeighborCompressor, params, a)
+    xs = [gen_input(40 + i, int(np.prod(s))).reshape(s) for i, s in enumerate(shapes)]
+    xs[0][3, 5] = np.nan
+    for p, x in zip(params, xs):
+        p.grad = torch.from_numpy(x).to(DEV)
+    q.record(0, epoch=0)
+    q.apply()
+    assert torch.isnan(params[0].grad).all()
+    assert torch.isfinite(params[1].grad).all()
