@@ -261,12 +261,13 @@ seg_absmax_ranges_kernel(const float *__restrict__ v, int64_t n, const int64_t *
     for (int64_t e0 = e_begin; e0 < e_end; e0 += 8 * span) {
         const int64_t e1 = min(e0 + span, e_end);
         float4 x[UN];
+        if (e0 + span <= e_end) {   // whole span inside the range (warp-uniform): UN independent loads in flight
 #pragma unroll
-        for (int t = 0; t < UN; ++t) {
-            const int64_t i0 = e0 + 4 * (lane + 32 * t);
-            if (i0 + 3 < e1) {
-                x[t] = ld_stream_f4(reinterpret_cast<const float4 *>(v + i0));
-            } else {
+            for (int t = 0; t < UN; ++t) x[t] = ld_stream_f4(reinterpret_cast<const float4 *>(v + e0 + 4 * (lane + 32 * t)));
+        } else {
+#pragma unroll
+            for (int t = 0; t < UN; ++t) {
+                const int64_t i0 = e0 + 4 * (lane + 32 * t);
                 float y[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) y[k] = (i0 + k < e1) ? v[i0 + k] : 0.0f;
@@ -321,12 +322,13 @@ qsgd_quantize_ranges_kernel(const float *__restrict__ v, int64_t n, const int64_
     for (int64_t e0 = e_begin; e0 < e_end; e0 += 8 * span) {
         const int64_t e1 = min(e0 + span, e_end);
         float4 x[UN];
+        if (e0 + span <= e_end) {   // whole span inside the range (warp-uniform): UN independent loads in flight
 #pragma unroll
-        for (int t = 0; t < UN; ++t) {
-            const int64_t i0 = e0 + 4 * (lane + 32 * t);
-            if (i0 + 3 < e1) {
-                x[t] = ld_stream_f4(reinterpret_cast<const float4 *>(v + i0));
-            } else {
+            for (int t = 0; t < UN; ++t) x[t] = ld_stream_f4(reinterpret_cast<const float4 *>(v + e0 + 4 * (lane + 32 * t)));
+        } else {
+#pragma unroll
+            for (int t = 0; t < UN; ++t) {
+                const int64_t i0 = e0 + 4 * (lane + 32 * t);
                 float y[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) y[k] = (i0 + k < e1) ? v[i0 + k] : 0.0f;
@@ -490,9 +492,12 @@ qsgd_decode_reduce_kernel(const float *__restrict__ norm, const void *__restrict
     }
 }
 
-// Fast decode-and-reduce: 8 consecutive elements per thread (one 32 / 64 / 128-bit word of packed
-// levels per user, two float4 stores), the chunk index from one 32-bit division per thread (or the
-// thread's cached segment), "/ s" and a power-of-two "/ U" as exact multiplications by 2^-k.
+// Fast decode-and-reduce: a warp decodes 256 elements at a time and lane L produces the float4 groups
+// L and 32 + L of the tile (two fully coalesced 512-byte stores).  4-bit fields: lane L loads the L-th
+// 32-bit word of every user (eight fields = two float4 groups) and the words are redistributed by
+// shuffles; 8- / 16-bit fields: a lane loads its own groups' words directly.  The chunk index is one
+// 32-bit division per float4 group (or the thread's cached segment), "/ s" and a power-of-two "/ U"
+// are exact multiplications by 2^-k.
 template <int BITS, int U_>   // U_ > 0: number of users at compile time
 __global__ void __launch_bounds__(256)
 qsgd_decode_reduce8_kernel(const float *__restrict__ norm, const void *__restrict__ packed, int64_t user_stride,
@@ -502,98 +507,108 @@ qsgd_decode_reduce8_kernel(const float *__restrict__ norm, const void *__restric
 {
     pdl_launch_dependents();
     const int n_users = U_ > 0 ? U_ : n_users_rt;
-    const int64_t n8 = n >> 3;
+    const int lane = threadIdx.x & 31;
+    const int64_t n_tiles = (n + 255) / 256;
     SegCache sc;
     pdl_wait();
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 255) {
-        // the last n % 8 elements, one by one
-        for (int64_t i = n8 * 8; i < n; ++i) {
-            const int m = chunk_start ? find_segment(chunk_start, n_chunks, i) : (int)((uint64_t)i / dim);
-            float acc = 0.0f;
-            for (int u = 0; u < n_users; ++u) {
-                const uint8_t *pu = reinterpret_cast<const uint8_t *>(packed) + u * user_stride;
-                const float *nu = reinterpret_cast<const float *>(reinterpret_cast<const char *>(norm) + u * user_stride);
-                uint32_t pk;
-                if (BITS == 4) pk = (pu[i >> 1] >> (4 * (i & 1))) & 15u;
-                else if (BITS == 8) pk = pu[i];
-                else pk = reinterpret_cast<const uint16_t *>(pu)[i];
-                const uint32_t sg = pk >> (BITS - 1);
-                const float lf = (float)(int)(pk & ((1u << (BITS - 1)) - 1u));
-                const float val = __fmul_rn(__fmul_rn(__fmul_rn(lf, sg ? 1.0f : -1.0f), nu[m]), inv_s);
-                acc = (u == 0) ? val : __fadd_rn(acc, val);
-            }
-            if (inv_u != 0.0f) acc = __fmul_rn(acc, inv_u);
-            else if (div_u != 0.0f) acc = __fdiv_rn(acc, div_u);
-            if (accumulate) acc = (accumulate == 2) ? __fsub_rn(out[i], acc) : __fadd_rn(out[i], acc);
-            out[i] = acc;
-        }
-    }
-    for (int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x; q < n8; q += (int64_t)gridDim.x * 256) {
-        const int64_t i0 = q * 8;
-        int m[8];
-        bool uni;
-        if (chunk_start) {
-            m[0] = cached_segment(sc, chunk_start, n_chunks, i0);
-            uni = i0 + 7 < sc.hi;
-            if (!uni) {
+    for (int64_t tile = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); tile < n_tiles; tile += (int64_t)gridDim.x * 8) {
+        const int64_t e0 = tile * 256;
+        if (e0 + 255 < n) {
+            // ---- full tile (warp-uniform) ----
+            int m[2];
+            bool uni[2];
 #pragma unroll
-                for (int t = 1; t < 8; ++t) m[t] = find_segment(chunk_start, n_chunks, i0 + t);
+            for (int t = 0; t < 2; ++t) {
+                const int64_t i0 = e0 + 4 * (t * 32 + lane);
+                if (chunk_start) {
+                    m[t] = cached_segment(sc, chunk_start, n_chunks, i0);
+                    uni[t] = i0 + 3 < sc.hi;
+                } else {
+                    m[t] = (int)((uint64_t)i0 / dim);
+                    uni[t] = (uint32_t)((uint64_t)i0 - (uint64_t)m[t] * dim) + 3u < dim;
+                }
+            }
+            float acc[2][4];
+#pragma unroll
+            for (int u = 0; u < (U_ > 0 ? U_ : 8); ++u) {
+                if (u >= n_users) break;
+                const char *pu = reinterpret_cast<const char *>(packed) + u * user_stride;
+                const float *nu = reinterpret_cast<const float *>(reinterpret_cast<const char *>(norm) + u * user_stride);
+                uint32_t w4 = 0u;
+                if (BITS == 4) w4 = __ldg(reinterpret_cast<const uint32_t *>(pu) + (e0 >> 3) + lane);
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    const int64_t g = (e0 >> 2) + t * 32 + lane;   // float4 group index
+                    uint32_t pk[4];
+                    if (BITS == 4) {
+                        const uint32_t ws = __shfl_sync(0xffffffffu, w4, t * 16 + (lane >> 1));
+                        const uint32_t h = (ws >> (16 * (lane & 1))) & 0xffffu;
+                        pk[0] = h & 15u; pk[1] = (h >> 4) & 15u; pk[2] = (h >> 8) & 15u; pk[3] = h >> 12;
+                    } else if (BITS == 8) {
+                        const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(pu) + g);
+                        pk[0] = w & 255u; pk[1] = (w >> 8) & 255u; pk[2] = (w >> 16) & 255u; pk[3] = w >> 24;
+                    } else {
+                        const uint2 w = __ldg(reinterpret_cast<const uint2 *>(pu) + g);
+                        pk[0] = w.x & 0xffffu; pk[1] = w.x >> 16; pk[2] = w.y & 0xffffu; pk[3] = w.y >> 16;
+                    }
+                    const float nm0 = __ldg(nu + m[t]);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        float nm = nm0;
+                        if (!uni[t]) {
+                            const int64_t i = e0 + 4 * (t * 32 + lane) + k;
+                            nm = __ldg(nu + (chunk_start ? find_segment(chunk_start, n_chunks, i) : (int)((uint64_t)i / dim)));
+                        }
+                        const uint32_t sg = pk[k] >> (BITS - 1);
+                        const float lf = (float)(int)(pk[k] & ((1u << (BITS - 1)) - 1u));
+                        // (float(l) * (2 * sign - 1)) * norm / s, qsgd_compressor.py:69-70
+                        const float val = __fmul_rn(__fmul_rn(__fmul_rn(lf, sg ? 1.0f : -1.0f), nm), inv_s);
+                        acc[t][k] = (u == 0) ? val : __fadd_rn(acc[t][k], val);
+                    }
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                float4 *op = reinterpret_cast<float4 *>(out + e0) + t * 32 + lane;
+                float r[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    r[k] = acc[t][k];
+                    if (inv_u != 0.0f) r[k] = __fmul_rn(r[k], inv_u);
+                    else if (div_u != 0.0f) r[k] = __fdiv_rn(r[k], div_u);
+                }
+                if (accumulate) {
+                    const float4 o = *op;
+                    r[0] = (accumulate == 2) ? __fsub_rn(o.x, r[0]) : __fadd_rn(o.x, r[0]);
+                    r[1] = (accumulate == 2) ? __fsub_rn(o.y, r[1]) : __fadd_rn(o.y, r[1]);
+                    r[2] = (accumulate == 2) ? __fsub_rn(o.z, r[2]) : __fadd_rn(o.z, r[2]);
+                    r[3] = (accumulate == 2) ? __fsub_rn(o.w, r[3]) : __fadd_rn(o.w, r[3]);
+                }
+                *op = make_float4(r[0], r[1], r[2], r[3]);
             }
         } else {
-            m[0] = (int)((uint64_t)i0 / dim);
-            uni = (uint32_t)((uint64_t)i0 - (uint64_t)m[0] * dim) + 7u < dim;
-            if (!uni) {
-#pragma unroll
-                for (int t = 1; t < 8; ++t) m[t] = (int)((uint64_t)(i0 + t) / dim);
+            // ---- the last, partial tile: element by element ----
+            for (int64_t i = e0 + lane; i < n; i += 32) {
+                const int mi = chunk_start ? find_segment(chunk_start, n_chunks, i) : (int)((uint64_t)i / dim);
+                float a = 0.0f;
+                for (int u = 0; u < n_users; ++u) {
+                    const uint8_t *pu = reinterpret_cast<const uint8_t *>(packed) + u * user_stride;
+                    const float *nu = reinterpret_cast<const float *>(reinterpret_cast<const char *>(norm) + u * user_stride);
+                    uint32_t pk;
+                    if (BITS == 4) pk = (pu[i >> 1] >> (4 * (i & 1))) & 15u;
+                    else if (BITS == 8) pk = pu[i];
+                    else pk = reinterpret_cast<const uint16_t *>(pu)[i];
+                    const uint32_t sg = pk >> (BITS - 1);
+                    const float lf = (float)(int)(pk & ((1u << (BITS - 1)) - 1u));
+                    const float val = __fmul_rn(__fmul_rn(__fmul_rn(lf, sg ? 1.0f : -1.0f), nu[mi]), inv_s);
+                    a = (u == 0) ? val : __fadd_rn(a, val);
+                }
+                if (inv_u != 0.0f) a = __fmul_rn(a, inv_u);
+                else if (div_u != 0.0f) a = __fdiv_rn(a, div_u);
+                if (accumulate) a = (accumulate == 2) ? __fsub_rn(out[i], a) : __fadd_rn(out[i], a);
+                out[i] = a;
             }
         }
-        float acc[8];
-#pragma unroll
-        for (int u = 0; u < (U_ > 0 ? U_ : 8); ++u) {
-            if (u >= n_users) break;
-            const char *pu = reinterpret_cast<const char *>(packed) + u * user_stride;
-            const float *nu = reinterpret_cast<const float *>(reinterpret_cast<const char *>(norm) + u * user_stride);
-            uint32_t pk[8];
-            if (BITS == 4) {
-                const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(pu) + q);
-#pragma unroll
-                for (int t = 0; t < 8; ++t) pk[t] = (w >> (4 * t)) & 15u;
-            } else if (BITS == 8) {
-                const uint2 w = __ldg(reinterpret_cast<const uint2 *>(pu) + q);
-#pragma unroll
-                for (int t = 0; t < 4; ++t) { pk[t] = (w.x >> (8 * t)) & 255u; pk[4 + t] = (w.y >> (8 * t)) & 255u; }
-            } else {
-                const uint4 w = __ldg(reinterpret_cast<const uint4 *>(pu) + q);
-                pk[0] = w.x & 0xffffu; pk[1] = w.x >> 16; pk[2] = w.y & 0xffffu; pk[3] = w.y >> 16;
-                pk[4] = w.z & 0xffffu; pk[5] = w.z >> 16; pk[6] = w.w & 0xffffu; pk[7] = w.w >> 16;
-            }
-            const float nm0 = __ldg(nu + m[0]);
-#pragma unroll
-            for (int t = 0; t < 8; ++t) {
-                const float nm = uni ? nm0 : __ldg(nu + m[t]);
-                const uint32_t sg = pk[t] >> (BITS - 1);
-                const float lf = (float)(int)(pk[t] & ((1u << (BITS - 1)) - 1u));
-                // (float(l) * (2 * sign - 1)) * norm / s, qsgd_compressor.py:69-70
-                const float val = __fmul_rn(__fmul_rn(__fmul_rn(lf, sg ? 1.0f : -1.0f), nm), inv_s);
-                acc[t] = (u == 0) ? val : __fadd_rn(acc[t], val);
-            }
-        }
-        float4 o[2];
-        float *of = reinterpret_cast<float *>(o);
-        if (accumulate) {
-            o[0] = reinterpret_cast<const float4 *>(out)[2 * q];
-            o[1] = reinterpret_cast<const float4 *>(out)[2 * q + 1];
-        }
-#pragma unroll
-        for (int t = 0; t < 8; ++t) {
-            float r = acc[t];
-            if (inv_u != 0.0f) r = __fmul_rn(r, inv_u);
-            else if (div_u != 0.0f) r = __fdiv_rn(r, div_u);
-            if (accumulate) r = (accumulate == 2) ? __fsub_rn(of[t], r) : __fadd_rn(of[t], r);
-            of[t] = r;
-        }
-        reinterpret_cast<float4 *>(out)[2 * q] = o[0];
-        reinterpret_cast<float4 *>(out)[2 * q + 1] = o[1];
     }
 }
 
@@ -619,7 +634,7 @@ int qsgd_decode_reduce(const float *norm, const void *packed, int64_t user_strid
         (user_stride & 15) == 0 && n < (1ll << 40) && n_chunks < (1ll << 31)) {
         float inv_u, div_u;
         mean_factors(mean, n_users, &inv_u, &div_u);
-        const int grid8 = grid_for(n8 + 1, 256, 16);
+        const int grid8 = grid_for((n + 255) / 256, 8, 16);
 #define GQ_D8(B, UU) GQ_CUDA(launch_pdl(qsgd_decode_reduce8_kernel<B, UU>, dim3(grid8), dim3(256), 0, st, norm, packed, user_stride, \
                                         n_users, n, chunk_start, (int)n_chunks, (uint32_t)(dim > 0 ? dim : 1), 1.0f / s, inv_u, div_u, accumulate, out))
 #define GQ_D8B(B) do { if (n_users == 1) GQ_D8(B, 1); else if (n_users == 2) GQ_D8(B, 2); else if (n_users == 4) GQ_D8(B, 4); \
@@ -702,7 +717,10 @@ sign_encode_kernel(const float *__restrict__ v, int64_t n, float *__restrict__ o
     }
 }
 
-// 16 elements per thread: one 32-bit word of packed signs per user, four float4 stores
+// A warp decodes 512 elements at a time: lane L loads the L-th 32-bit word of packed signs of every
+// user (one coalesced 128-byte request per user), the words are redistributed by shuffles so that lane
+// L produces the float4 groups L, 32 + L, 64 + L, 96 + L of the tile: four fully coalesced 512-byte
+// stores (a thread writing its own 16 consecutive elements would put half-sector writes on L2).
 template <int U_>
 __global__ void __launch_bounds__(256)
 sign_decode_reduce_kernel(const uint8_t *__restrict__ packed, int64_t user_stride, int n_users_rt,
@@ -710,41 +728,46 @@ sign_decode_reduce_kernel(const uint8_t *__restrict__ packed, int64_t user_strid
 {
     pdl_launch_dependents();
     const int n_users = U_ > 0 ? U_ : n_users_rt;
-    const int64_t n16 = (n + 15) / 16;
+    const int lane = threadIdx.x & 31;
+    const int64_t n_tiles = (n + 511) / 512;
     const bool aligned = ((reinterpret_cast<uintptr_t>(out) & 15) == 0) && ((user_stride & 3) == 0) &&
                          ((reinterpret_cast<uintptr_t>(packed) & 3) == 0);
     pdl_wait();
-    for (int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x; q < n16; q += (int64_t)gridDim.x * 256) {
-        const int64_t i0 = q * 16;
-        const bool full = aligned && (i0 + 15 < n);
-        float acc[16];
+    for (int64_t tile = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); tile < n_tiles; tile += (int64_t)gridDim.x * 8) {
+        const int64_t e0 = tile * 512;
+        const bool full = aligned && (e0 + 511 < n);   // warp-uniform
+        float acc[4][4];
         for (int u = 0; u < n_users; ++u) {
-            const uint8_t *pu = packed + u * user_stride;
-            uint32_t w;
+            const uint8_t *pu = packed + u * user_stride + (e0 >> 2);
+            uint32_t w = 0u;
             if (full) {
-                w = __ldg(reinterpret_cast<const uint32_t *>(pu) + q);
+                w = __ldg(reinterpret_cast<const uint32_t *>(pu) + lane);
             } else {
-                w = 0u;
                 for (int k = 0; k < 4; ++k)
-                    if (i0 + 4 * k < n) w |= (uint32_t)pu[q * 4 + k] << (8 * k);
+                    if (e0 + 16 * lane + 4 * k < n) w |= (uint32_t)pu[4 * lane + k] << (8 * k);
             }
 #pragma unroll
-            for (int t = 0; t < 16; ++t) {
-                const uint32_t c = (w >> (2 * t)) & 3u;
-                const float val = (c & 1u) ? 1.0f : ((c & 2u) ? -1.0f : 0.0f);
-                acc[t] = (u == 0) ? val : __fadd_rn(acc[t], val);
+            for (int t = 0; t < 4; ++t) {
+                const uint32_t ws = __shfl_sync(0xffffffffu, w, t * 8 + (lane >> 2));
+                const uint32_t by = (ws >> (8 * (lane & 3))) & 0xffu;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t c = (by >> (2 * k)) & 3u;
+                    const float val = (c & 1u) ? 1.0f : ((c & 2u) ? -1.0f : 0.0f);
+                    acc[t][k] = (u == 0) ? val : __fadd_rn(acc[t][k], val);
+                }
             }
         }
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int t = 0; t < 4; ++t) {
             float r[4];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                r[t] = acc[4 * g + t];
-                if (inv_u != 0.0f) r[t] = __fmul_rn(r[t], inv_u);
-                else if (div_u != 0.0f) r[t] = __fdiv_rn(r[t], div_u);
+            for (int k = 0; k < 4; ++k) {
+                r[k] = acc[t][k];
+                if (inv_u != 0.0f) r[k] = __fmul_rn(r[k], inv_u);
+                else if (div_u != 0.0f) r[k] = __fdiv_rn(r[k], div_u);
             }
-            const int64_t i = i0 + 4 * g;
+            const int64_t i = e0 + 4 * (t * 32 + lane);
             if (full) {
                 float4 *op = reinterpret_cast<float4 *>(out + i);
                 if (accumulate) {
@@ -757,11 +780,11 @@ sign_decode_reduce_kernel(const uint8_t *__restrict__ packed, int64_t user_strid
                 *op = make_float4(r[0], r[1], r[2], r[3]);
             } else {
 #pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    if (i + t >= n) continue;
-                    float x = r[t];
-                    if (accumulate) x = (accumulate == 2) ? __fsub_rn(out[i + t], x) : __fadd_rn(out[i + t], x);
-                    out[i + t] = x;
+                for (int k = 0; k < 4; ++k) {
+                    if (i + k >= n) continue;
+                    float x = r[k];
+                    if (accumulate) x = (accumulate == 2) ? __fsub_rn(out[i + k], x) : __fadd_rn(out[i + k], x);
+                    out[i + k] = x;
                 }
             }
         }
@@ -782,7 +805,7 @@ int sign_decode_reduce(const uint8_t *packed, int64_t user_stride, int n_users, 
     if (n == 0) return GQ_OK;
     float inv_u, div_u;
     mean_factors(mean, n_users, &inv_u, &div_u);
-    const int grid = grid_for((n + 15) / 16, 256, 16);
+    const int grid = grid_for((n + 511) / 512, 8, 16);
 #define GQ_S(UU) GQ_CUDA(launch_pdl(sign_decode_reduce_kernel<UU>, dim3(grid), dim3(256), 0, st, packed, user_stride, n_users, n, \
                                     inv_u, div_u, accumulate, out))
     if (n_users == 1) GQ_S(1);
