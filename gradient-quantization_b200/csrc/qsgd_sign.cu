@@ -62,6 +62,18 @@ __device__ __forceinline__ int qsgd_level(float x, float nm, float s, int random
     return li;
 }
 
+// same, for the packed wire form (which has no room for the reference's INT_MIN level of a 0/0
+// element: a NaN quotient gives level 0 through the same arithmetic -- fmaxf(NaN, 0) = 0 and
+// NaN > r is false -- so no branch is needed)
+__device__ __forceinline__ uint32_t qsgd_level_packed(float x, float nm, float s, int random, float r)
+{
+    const float scaled = fabsf(__fdiv_rn(x, nm)) * s;
+    const float c = fminf(fmaxf(scaled, 0.0f), s - 1.0f);
+    int li = (int)c;
+    li += (random && (__fsub_rn(scaled, (float)li) > r)) ? 1 : 0;
+    return (uint32_t)li;
+}
+
 template <int BITS>  // 0: no packed output; 4, 8, 16
 __global__ void __launch_bounds__(256)
 qsgd_quantize_kernel(const float *__restrict__ v, int64_t n, const int64_t *__restrict__ chunk_start,
@@ -219,11 +231,8 @@ qsgd_encode_chunks_kernel(const float *__restrict__ v, int64_t n_chunks, int dim
                 const float xe[4] = {x[u][t].x, x[u][t].y, x[u][t].z, x[u][t].w};
                 uint32_t pk[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    bool is_nan;
-                    const int li = qsgd_level(xe[e], nm, s, random, r[e], is_nan);
-                    pk[e] = ((xe[e] > 0.0f ? 1u : 0u) << (BITS - 1)) | (uint32_t)li;
-                }
+                for (int e = 0; e < 4; ++e)
+                    pk[e] = ((xe[e] > 0.0f ? 1u : 0u) << (BITS - 1)) | qsgd_level_packed(xe[e], nm, s, random, r[e]);
                 qsgd_store_packed<BITS>(packed, q, pk);
             }
         }
@@ -346,7 +355,7 @@ qsgd_quantize_ranges_kernel(const float *__restrict__ v, int64_t n, const int64_
             const int64_t i0 = e0 + 4 * (lane + 32 * t);
             if (i0 >= e1) continue;
             float r[4];
-            if (i0 + 3 < n) {
+            if (i0 + 3 < n) {   // (always, except in the last float4 group of the gradient)
                 qsgd_uniforms4(random, uniforms, seed, offset, i0, r);
             } else {
 #pragma unroll
@@ -356,13 +365,17 @@ qsgd_quantize_ranges_kernel(const float *__restrict__ v, int64_t n, const int64_
             }
             const float y[4] = {x[t].x, x[t].y, x[t].z, x[t].w};
             uint32_t pk[4];
+            if (uniform && i0 + 3 < e1) {   // the common case: four elements of one tensor, no per-element branches
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (i0 + k >= e1) { pk[k] = 0u; continue; }
-                const float nm = uniform ? nm_cur : __ldcg(norm + find_segment(chunk_start, n_chunks, i0 + k));
-                bool is_nan;
-                const int li = qsgd_level(y[k], nm, s, random, r[k], is_nan);
-                pk[k] = ((y[k] > 0.0f ? 1u : 0u) << (BITS - 1)) | (uint32_t)li;
+                for (int k = 0; k < 4; ++k)
+                    pk[k] = ((y[k] > 0.0f ? 1u : 0u) << (BITS - 1)) | qsgd_level_packed(y[k], nm_cur, s, random, r[k]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (i0 + k >= e1) { pk[k] = 0u; continue; }
+                    const float nm = uniform ? nm_cur : __ldcg(norm + find_segment(chunk_start, n_chunks, i0 + k));
+                    pk[k] = ((y[k] > 0.0f ? 1u : 0u) << (BITS - 1)) | qsgd_level_packed(y[k], nm, s, random, r[k]);
+                }
             }
             qsgd_store_packed<BITS>(packed, i0 >> 2, pk);
         }
