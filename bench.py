@@ -212,33 +212,72 @@ ORIG_AFFINITY = None
 
 
 def bind_to_gpu_numa(index):
-    """Pin this process to the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned host buffer
-    is allocated (first touch then places the pages there).  Round 1's end-to-end number did not
-    scale (46 -> 8 GB/s per GPU from N = 1 to 8) because every rank's pinned buffers sat on node 0.
-    Returns a short description for the JSON line; never fails the run."""
+    """Place this rank's pinned host buffers on the NUMA node its GPU hangs off, BEFORE any of them is
+    allocated: CPU affinity to that node's cores (first touch) and, where the kernel allows it, a
+    preferred-node memory policy.  Round 1's end-to-end number did not scale (46 -> 8 GB/s per GPU from
+    N = 1 to 8) because every rank's pinned buffers sat on node 0.  The node comes from sysfs, else from
+    NVML's memory / CPU affinity of the device.  Returns a short description for the JSON line; never
+    fails the run."""
+    global ORIG_AFFINITY
+    note = []
     try:
         import pynvml
         pynvml.nvmlInit()
         h = pynvml.nvmlDeviceGetHandleByIndex(index)
-        bdf = pynvml.nvmlDeviceGetPciInfo(h).busId
-        bdf = (bdf.decode() if isinstance(bdf, bytes) else bdf).lower()
-        if len(bdf.split(":")[0]) == 8:          # nvml pads the domain to 8 hex digits, sysfs uses 4
-            bdf = bdf[4:]
-        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as fh:
-            node = int(fh.read().strip())
+        node = -1
+        try:
+            bdf = pynvml.nvmlDeviceGetPciInfo(h).busId
+            bdf = (bdf.decode() if isinstance(bdf, bytes) else bdf).lower()
+            if len(bdf.split(":")[0]) == 8:          # nvml pads the domain to 8 hex digits, sysfs uses 4
+                bdf = bdf[4:]
+            with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as fh:
+                node = int(fh.read().strip())
+        except Exception:  # noqa: BLE001
+            node = -1
         if node < 0:
-            return "numa node unknown"
-        with open("/sys/devices/system/node/node%d/cpulist" % node) as fh:
-            cpus = set()
-            for part in fh.read().strip().split(","):
-                lo, _, hi = part.partition("-")
-                cpus.update(range(int(lo), int(hi or lo) + 1))
-        global ORIG_AFFINITY
+            try:                                      # NVML: bit mask of the NUMA nodes closest to the device
+                mask = pynvml.nvmlDeviceGetMemoryAffinity(h, 4, 0)
+                bits = [64 * w + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1]
+                if bits:
+                    node = bits[0]
+                    note.append("node from NVML")
+            except Exception:  # noqa: BLE001
+                pass
+        cpus = set()
+        if node >= 0:
+            try:
+                with open("/sys/devices/system/node/node%d/cpulist" % node) as fh:
+                    for part in fh.read().strip().split(","):
+                        lo, _, hi = part.partition("-")
+                        cpus.update(range(int(lo), int(hi or lo) + 1))
+            except Exception:  # noqa: BLE001
+                pass
+        if not cpus:
+            try:                                      # NVML: the device's ideal CPU set
+                words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+                cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+                if cpus:
+                    note.append("cpus from NVML")
+            except Exception:  # noqa: BLE001
+                pass
         ORIG_AFFINITY = set(os.sched_getaffinity(0))
         allowed = cpus & ORIG_AFFINITY
-        if allowed:
+        if allowed and allowed != ORIG_AFFINITY:
             os.sched_setaffinity(0, allowed)
-        return "bound to NUMA node %d (%d cpus)" % (node, len(allowed))
+            note.append("%d cpus" % len(allowed))
+        elif cpus and not allowed:
+            note.append("the node's cpus are outside this container's cpuset")
+        if node >= 0:
+            try:                                      # set_mempolicy(MPOL_PREFERRED, {node}) -- x86-64 syscall 238
+                import ctypes
+                libc = ctypes.CDLL(None, use_errno=True)
+                nodemask = ctypes.c_ulong(1 << node)
+                rc = libc.syscall(238, 1, ctypes.byref(nodemask), ctypes.c_ulong(65))
+                note.append("mempolicy preferred" if rc == 0 else "mempolicy refused (errno %d)" % ctypes.get_errno())
+            except Exception:  # noqa: BLE001
+                pass
+            return "NUMA node %d (%s)" % (node, ", ".join(note) or "no binding possible")
+        return "numa node unknown" + (" (%s)" % ", ".join(note) if note else "")
     except Exception as e:  # noqa: BLE001
         return "not bound (%s)" % type(e).__name__
 

@@ -755,159 +755,6 @@ hsq_decode_reduce_staged_kernel(const uint8_t *__restrict__ codes, const uint8_t
     }
 }
 
-// Decode-and-average for three or more users: every lane OWNS one chunk (four float4 accumulators)
-// and walks the users itself -- per user two byte loads from the stage, one dequantized norm and the
-// whole codeword (four LDS.128) -- instead of sharing a chunk between four lanes: no shuffles, no
-// norm computed four times (the staged kernel executes 772 warp instructions per 32 chunks at U = 8,
-// this one about 330).  The codebook sits in shared memory as four rotated planes with every 64-byte
-// codeword stored twice in a 128-byte slot (plane = (lane & 7) >> 1, half = lane & 1), so that the
-// eight lanes of a quarter-warp read eight different 16-byte bank groups whatever their codewords.
-constexpr int kOwnerThreads = 512;   // one CTA per SM (165 KB of shared memory): sixteen warps
-template <int NU>
-__global__ void __launch_bounds__(kOwnerThreads)
-hsq_decode_reduce_owner_kernel(const uint8_t *__restrict__ codes, const uint8_t *__restrict__ l,
-                               const float *__restrict__ lbub, const UserOffsets uoff,
-                               int64_t n_chunks, const float *__restrict__ codebook,
-                               const int64_t *__restrict__ seg_start, int n_seg, float s, int mean,
-                               int accumulate, float *__restrict__ out, const Rider rider, const PeerWait wait)
-{
-    extern __shared__ float4 s_dyn[];
-    float4 *s_cb = s_dyn;                                                    // [4 planes][256][2 halves][4 units]
-    uint8_t *s_stage = reinterpret_cast<uint8_t *>(s_cb + 4 * 256 * 8);      // [2][NU][codes 1024 | l 1024]
-    float2 *s_lbub = reinterpret_cast<float2 *>(s_stage + 2 * NU * 2 * kStTile);   // [NU][n_seg]
-    __shared__ int64_t s_off[8];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    pdl_launch_dependents();
-    if (tid == 0) {
-#pragma unroll
-        for (int u = 0; u < 8; ++u) s_off[u] = uoff.off[u];
-    }
-    for (int i = tid; i < 4 * 256 * 8; i += kOwnerThreads) {
-        const int u = i & 3, h = (i >> 2) & 1, k = (i >> 3) & 255, r = i >> 11;
-        s_cb[r * 2048 + k * 8 + 4 * h + ((u + r) & 3)] = __ldg(reinterpret_cast<const float4 *>(codebook) + k * 4 + u);
-    }
-    __syncthreads();
-    pdl_wait();
-    if (wait.n > 0) {
-        if (tid < wait.n) peer_wait_flag(wait.flags + tid, wait.epoch, wait.timeout_ns);
-        __syncthreads();
-    }
-    const int64_t n_tiles = (n_chunks + kStTile - 1) / kStTile;
-    auto issue = [&](int64_t tile, int buf) {
-        const int64_t c0 = tile * kStTile;
-        const int64_t left = n_chunks - c0;
-        const int pieces = (int)(((left < kStTile ? left : (int64_t)kStTile) + 15) >> 4);
-        for (int i = tid; i < NU * 128; i += kOwnerThreads) {
-            const int u = i >> 7, which = (i >> 6) & 1, piece = i & 63;
-            if (piece < pieces) {
-                const char *src = (which ? reinterpret_cast<const char *>(l) : reinterpret_cast<const char *>(codes)) +
-                                  s_off[u] + c0 + piece * 16;
-                cp_async16(s_stage + ((buf * NU + u) * 2 + which) * kStTile + piece * 16, src);
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    const float inv_s = 1.0f / s;
-    const float nu = (float)NU;
-    constexpr bool pow2 = (NU & (NU - 1)) == 0;
-    const float inv_nu = 1.0f / nu;
-    const int rot = (lane & 7) >> 1, hlf = lane & 1;
-    const uint32_t cb_lane = (uint32_t)__cvta_generic_to_shared(s_cb) + (uint32_t)(rot * 32768 + hlf * 64);
-    uint32_t uo[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) uo[u] = 16u * ((u + rot) & 3);
-    const uint32_t stage0 = (uint32_t)__cvta_generic_to_shared(s_stage);
-    SegCache segc;
-    float4 *o4 = reinterpret_cast<float4 *>(out);
-    int64_t tile = blockIdx.x;
-    int buf = 0;
-    if (tile < n_tiles) issue(tile, 0);
-    for (int i = tid; i < NU * n_seg; i += kOwnerThreads) {
-        const int u = i / n_seg, sg = i - u * n_seg;
-        const float2 *b = reinterpret_cast<const float2 *>(reinterpret_cast<const char *>(lbub) + s_off[u]);
-        s_lbub[i] = __ldcv(b + sg);
-    }
-    rider_run(rider, (int64_t)blockIdx.x * kOwnerThreads + tid, (int64_t)gridDim.x * kOwnerThreads);
-    for (; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
-        const int64_t next = tile + gridDim.x;
-        if (next < n_tiles) {
-            issue(next, buf ^ 1);
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-        } else {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-        }
-        __syncthreads();
-        const uint32_t st = stage0 + (uint32_t)(buf * NU * 2 * kStTile);
-        const int64_t c0 = tile * kStTile;
-        for (int sl = warp; sl < kStTile / 32; sl += kOwnerThreads / 32) {
-            const int64_t c = c0 + sl * 32 + lane;
-            if (c >= n_chunks) continue;
-            const int seg = cached_segment(segc, seg_start, n_seg, c);
-            float4 acc[4];
-#pragma unroll
-            for (int u = 0; u < NU; ++u) {
-                const uint32_t cb8 = lds_u8(st + (uint32_t)((u * 2) * kStTile + sl * 32 + lane));
-                const uint32_t lv8 = lds_u8(st + (uint32_t)((u * 2 + 1) * kStTile + sl * 32 + lane));
-                const float2 b = s_lbub[u * n_seg + seg];
-                // l * (ub - lb) / 2^n + lb   (probabilistic_scalar_compressor.py:31-32)
-                const float nm = __fadd_rn(__fmul_rn(__fmul_rn((float)(int)lv8, __fsub_rn(b.y, b.x)), inv_s), b.x);
-                const uint32_t slot = cb_lane + (cb8 << 7);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float4 cw = lds128(slot + uo[q]);
-                    const float2 p0 = mul2(make_float2(cw.x, cw.y), nm);
-                    const float2 p1 = mul2(make_float2(cw.z, cw.w), nm);
-                    if (u == 0) {
-                        acc[q] = make_float4(p0.x, p0.y, p1.x, p1.y);
-                    } else {   // scalar adds in user order: see hsq_decode_reduce_warp_kernel
-                        acc[q].x = __fadd_rn(acc[q].x, p0.x); acc[q].y = __fadd_rn(acc[q].y, p0.y);
-                        acc[q].z = __fadd_rn(acc[q].z, p1.x); acc[q].w = __fadd_rn(acc[q].w, p1.y);
-                    }
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                float4 a = acc[q];
-                if (mean) {
-                    if (pow2) {
-                        a.x = __fmul_rn(a.x, inv_nu); a.y = __fmul_rn(a.y, inv_nu);
-                        a.z = __fmul_rn(a.z, inv_nu); a.w = __fmul_rn(a.w, inv_nu);
-                    } else {
-                        a.x = __fdiv_rn(a.x, nu); a.y = __fdiv_rn(a.y, nu);
-                        a.z = __fdiv_rn(a.z, nu); a.w = __fdiv_rn(a.w, nu);
-                    }
-                }
-                if (accumulate) a = combine4(o4[c * 4 + q], a, accumulate);
-                o4[c * 4 + q] = a;
-            }
-        }
-        __syncthreads();
-    }
-}
-
-template <int NU>
-static int launch_decode_owner(const void *codes, const void *l, const float *lbub, const UserOffsets &uoff,
-                               int64_t n_chunks, const float *codebook, const int64_t *seg_start,
-                               int n_seg, float s, int mean, int accumulate, float *out, cudaStream_t st)
-{
-    auto kern = hsq_decode_reduce_owner_kernel<NU>;
-    const size_t smem = 4 * 256 * 128 + (size_t)2 * NU * 2 * kStTile + (size_t)NU * n_seg * 8;
-    GQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 1;
-    GQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kOwnerThreads, smem));
-    const int64_t n_tiles = (n_chunks + kStTile - 1) / kStTile;
-    const int64_t cap = (int64_t)sm_count() * (occ < 1 ? 1 : occ);
-    const int64_t per = (n_tiles + cap - 1) / cap;
-    int64_t grid = (n_tiles + per - 1) / per;
-    if (grid < 1) grid = 1;
-    const Rider rider = take_rider();
-    const PeerWait wait = take_wait();
-    GQ_CUDA(launch_pdl(kern, dim3((unsigned)grid), dim3(kOwnerThreads), smem, st, (const uint8_t *)codes,
-                       (const uint8_t *)l, lbub, uoff, n_chunks, codebook, seg_start, n_seg, s, mean,
-                       accumulate, out, rider, wait));
-    return GQ_OK;
-}
-
 template <int NU>
 static int launch_decode_staged(const void *codes, const void *l, const float *lbub, const UserOffsets &uoff,
                                 int64_t n_chunks, const float *codebook, const int64_t *seg_start,
@@ -980,17 +827,6 @@ static int launch_decode_d(const void *codes, const void *l, const float *lbub, 
             bool aligned = (((uintptr_t)codes | (uintptr_t)l | (uintptr_t)lbub) & 15) == 0;
             for (int u = 0; u < n_users; ++u) aligned = aligned && ((uoff.off[u] & 15) == 0);
             if (aligned) {
-                // three or more users: the lane-owns-chunk kernel (GQ_DECODE_OWNER=0: the staged one)
-                bool owner = n_users >= 3 && (size_t)4 * 256 * 128 + (size_t)4 * n_users * kStTile + (size_t)n_users * n_seg * 8 <= 220 * 1024;
-                if (const char *e = getenv("GQ_DECODE_OWNER")) owner = owner && atoi(e) != 0;
-#define GQ_O(MU) case MU: return launch_decode_owner<MU>(codes, l, lbub, uoff, n_chunks, codebook, seg_start, n_seg, s, mean, accumulate, out, st)
-                if (owner) {
-                    switch (n_users) {
-                        GQ_O(3); GQ_O(4); GQ_O(5); GQ_O(6); GQ_O(7); GQ_O(8);
-                        default: break;
-                    }
-                }
-#undef GQ_O
 #define GQ_S(MU) case MU: return launch_decode_staged<MU>(codes, l, lbub, uoff, n_chunks, codebook, seg_start, n_seg, s, mean, accumulate, out, st)
                 switch (n_users) {
                     GQ_S(1); GQ_S(2); GQ_S(3); GQ_S(4); GQ_S(5); GQ_S(6); GQ_S(7); GQ_S(8);

@@ -505,12 +505,9 @@ qsgd_decode_reduce_kernel(const float *__restrict__ norm, const void *__restrict
     }
 }
 
-// Fast decode-and-reduce: a warp decodes 256 elements at a time and lane L produces the float4 groups
-// L and 32 + L of the tile (two fully coalesced 512-byte stores).  4-bit fields: lane L loads the L-th
-// 32-bit word of every user (eight fields = two float4 groups) and the words are redistributed by
-// shuffles; 8- / 16-bit fields: a lane loads its own groups' words directly.  The chunk index is one
-// 32-bit division per float4 group (or the thread's cached segment), "/ s" and a power-of-two "/ U"
-// are exact multiplications by 2^-k.
+// Fast decode-and-reduce: 8 consecutive elements per thread (one 32 / 64 / 128-bit word of packed
+// levels per user, two float4 stores), the chunk index from one 32-bit division per thread (or the
+// thread's cached segment), "/ s" and a power-of-two "/ U" as exact multiplications by 2^-k.
 template <int BITS, int U_>   // U_ > 0: number of users at compile time
 __global__ void __launch_bounds__(256)
 qsgd_decode_reduce8_kernel(const float *__restrict__ norm, const void *__restrict__ packed, int64_t user_stride,
@@ -520,108 +517,98 @@ qsgd_decode_reduce8_kernel(const float *__restrict__ norm, const void *__restric
 {
     pdl_launch_dependents();
     const int n_users = U_ > 0 ? U_ : n_users_rt;
-    const int lane = threadIdx.x & 31;
-    const int64_t n_tiles = (n + 255) / 256;
+    const int64_t n8 = n >> 3;
     SegCache sc;
     pdl_wait();
-    for (int64_t tile = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); tile < n_tiles; tile += (int64_t)gridDim.x * 8) {
-        const int64_t e0 = tile * 256;
-        if (e0 + 255 < n) {
-            // ---- full tile (warp-uniform) ----
-            int m[2];
-            bool uni[2];
-#pragma unroll
-            for (int t = 0; t < 2; ++t) {
-                const int64_t i0 = e0 + 4 * (t * 32 + lane);
-                if (chunk_start) {
-                    m[t] = cached_segment(sc, chunk_start, n_chunks, i0);
-                    uni[t] = i0 + 3 < sc.hi;
-                } else {
-                    m[t] = (int)((uint64_t)i0 / dim);
-                    uni[t] = (uint32_t)((uint64_t)i0 - (uint64_t)m[t] * dim) + 3u < dim;
-                }
-            }
-            float acc[2][4];
-#pragma unroll
-            for (int u = 0; u < (U_ > 0 ? U_ : 8); ++u) {
-                if (u >= n_users) break;
-                const char *pu = reinterpret_cast<const char *>(packed) + u * user_stride;
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 255) {
+        // the last n % 8 elements, one by one
+        for (int64_t i = n8 * 8; i < n; ++i) {
+            const int m = chunk_start ? find_segment(chunk_start, n_chunks, i) : (int)((uint64_t)i / dim);
+            float acc = 0.0f;
+            for (int u = 0; u < n_users; ++u) {
+                const uint8_t *pu = reinterpret_cast<const uint8_t *>(packed) + u * user_stride;
                 const float *nu = reinterpret_cast<const float *>(reinterpret_cast<const char *>(norm) + u * user_stride);
-                uint32_t w4 = 0u;
-                if (BITS == 4) w4 = __ldg(reinterpret_cast<const uint32_t *>(pu) + (e0 >> 3) + lane);
-#pragma unroll
-                for (int t = 0; t < 2; ++t) {
-                    const int64_t g = (e0 >> 2) + t * 32 + lane;   // float4 group index
-                    uint32_t pk[4];
-                    if (BITS == 4) {
-                        const uint32_t ws = __shfl_sync(0xffffffffu, w4, t * 16 + (lane >> 1));
-                        const uint32_t h = (ws >> (16 * (lane & 1))) & 0xffffu;
-                        pk[0] = h & 15u; pk[1] = (h >> 4) & 15u; pk[2] = (h >> 8) & 15u; pk[3] = h >> 12;
-                    } else if (BITS == 8) {
-                        const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(pu) + g);
-                        pk[0] = w & 255u; pk[1] = (w >> 8) & 255u; pk[2] = (w >> 16) & 255u; pk[3] = w >> 24;
-                    } else {
-                        const uint2 w = __ldg(reinterpret_cast<const uint2 *>(pu) + g);
-                        pk[0] = w.x & 0xffffu; pk[1] = w.x >> 16; pk[2] = w.y & 0xffffu; pk[3] = w.y >> 16;
-                    }
-                    const float nm0 = __ldg(nu + m[t]);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        float nm = nm0;
-                        if (!uni[t]) {
-                            const int64_t i = e0 + 4 * (t * 32 + lane) + k;
-                            nm = __ldg(nu + (chunk_start ? find_segment(chunk_start, n_chunks, i) : (int)((uint64_t)i / dim)));
-                        }
-                        const uint32_t sg = pk[k] >> (BITS - 1);
-                        const float lf = (float)(int)(pk[k] & ((1u << (BITS - 1)) - 1u));
-                        // (float(l) * (2 * sign - 1)) * norm / s, qsgd_compressor.py:69-70
-                        const float val = __fmul_rn(__fmul_rn(__fmul_rn(lf, sg ? 1.0f : -1.0f), nm), inv_s);
-                        acc[t][k] = (u == 0) ? val : __fadd_rn(acc[t][k], val);
-                    }
-                }
+                uint32_t pk;
+                if (BITS == 4) pk = (pu[i >> 1] >> (4 * (i & 1))) & 15u;
+                else if (BITS == 8) pk = pu[i];
+                else pk = reinterpret_cast<const uint16_t *>(pu)[i];
+                const uint32_t sg = pk >> (BITS - 1);
+                const float lf = (float)(int)(pk & ((1u << (BITS - 1)) - 1u));
+                const float val = __fmul_rn(__fmul_rn(__fmul_rn(lf, sg ? 1.0f : -1.0f), nu[m]), inv_s);
+                acc = (u == 0) ? val : __fadd_rn(acc, val);
             }
+            if (inv_u != 0.0f) acc = __fmul_rn(acc, inv_u);
+            else if (div_u != 0.0f) acc = __fdiv_rn(acc, div_u);
+            if (accumulate) acc = (accumulate == 2) ? __fsub_rn(out[i], acc) : __fadd_rn(out[i], acc);
+            out[i] = acc;
+        }
+    }
+    for (int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x; q < n8; q += (int64_t)gridDim.x * 256) {
+        const int64_t i0 = q * 8;
+        int m[8];
+        bool uni;
+        if (chunk_start) {
+            m[0] = cached_segment(sc, chunk_start, n_chunks, i0);
+            uni = i0 + 7 < sc.hi;
+            if (!uni) {
 #pragma unroll
-            for (int t = 0; t < 2; ++t) {
-                float4 *op = reinterpret_cast<float4 *>(out + e0) + t * 32 + lane;
-                float r[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    r[k] = acc[t][k];
-                    if (inv_u != 0.0f) r[k] = __fmul_rn(r[k], inv_u);
-                    else if (div_u != 0.0f) r[k] = __fdiv_rn(r[k], div_u);
-                }
-                if (accumulate) {
-                    const float4 o = *op;
-                    r[0] = (accumulate == 2) ? __fsub_rn(o.x, r[0]) : __fadd_rn(o.x, r[0]);
-                    r[1] = (accumulate == 2) ? __fsub_rn(o.y, r[1]) : __fadd_rn(o.y, r[1]);
-                    r[2] = (accumulate == 2) ? __fsub_rn(o.z, r[2]) : __fadd_rn(o.z, r[2]);
-                    r[3] = (accumulate == 2) ? __fsub_rn(o.w, r[3]) : __fadd_rn(o.w, r[3]);
-                }
-                *op = make_float4(r[0], r[1], r[2], r[3]);
+                for (int t = 1; t < 8; ++t) m[t] = find_segment(chunk_start, n_chunks, i0 + t);
             }
         } else {
-            // ---- the last, partial tile: element by element ----
-            for (int64_t i = e0 + lane; i < n; i += 32) {
-                const int mi = chunk_start ? find_segment(chunk_start, n_chunks, i) : (int)((uint64_t)i / dim);
-                float a = 0.0f;
-                for (int u = 0; u < n_users; ++u) {
-                    const uint8_t *pu = reinterpret_cast<const uint8_t *>(packed) + u * user_stride;
-                    const float *nu = reinterpret_cast<const float *>(reinterpret_cast<const char *>(norm) + u * user_stride);
-                    uint32_t pk;
-                    if (BITS == 4) pk = (pu[i >> 1] >> (4 * (i & 1))) & 15u;
-                    else if (BITS == 8) pk = pu[i];
-                    else pk = reinterpret_cast<const uint16_t *>(pu)[i];
-                    const uint32_t sg = pk >> (BITS - 1);
-                    const float lf = (float)(int)(pk & ((1u << (BITS - 1)) - 1u));
-                    const float val = __fmul_rn(__fmul_rn(__fmul_rn(lf, sg ? 1.0f : -1.0f), nu[mi]), inv_s);
-                    a = (u == 0) ? val : __fadd_rn(a, val);
-                }
-                if (inv_u != 0.0f) a = __fmul_rn(a, inv_u);
-                else if (div_u != 0.0f) a = __fdiv_rn(a, div_u);
-                if (accumulate) a = (accumulate == 2) ? __fsub_rn(out[i], a) : __fadd_rn(out[i], a);
-                out[i] = a;
+            m[0] = (int)((uint64_t)i0 / dim);
+            uni = (uint32_t)((uint64_t)i0 - (uint64_t)m[0] * dim) + 7u < dim;
+            if (!uni) {
+#pragma unroll
+                for (int t = 1; t < 8; ++t) m[t] = (int)((uint64_t)(i0 + t) / dim);
             }
         }
+        float acc[8];
+#pragma unroll
+        for (int u = 0; u < (U_ > 0 ? U_ : 8); ++u) {
+            if (u >= n_users) break;
+            const char *pu = reinterpret_cast<const char *>(packed) + u * user_stride;
+            const float *nu = reinterpret_cast<const float *>(reinterpret_cast<const char *>(norm) + u * user_stride);
+            uint32_t pk[8];
+            if (BITS == 4) {
+                const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(pu) + q);
+#pragma unroll
+                for (int t = 0; t < 8; ++t) pk[t] = (w >> (4 * t)) & 15u;
+            } else if (BITS == 8) {
+                const uint2 w = __ldg(reinterpret_cast<const uint2 *>(pu) + q);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) { pk[t] = (w.x >> (8 * t)) & 255u; pk[4 + t] = (w.y >> (8 * t)) & 255u; }
+            } else {
+                const uint4 w = __ldg(reinterpret_cast<const uint4 *>(pu) + q);
+                pk[0] = w.x & 0xffffu; pk[1] = w.x >> 16; pk[2] = w.y & 0xffffu; pk[3] = w.y >> 16;
+                pk[4] = w.z & 0xffffu; pk[5] = w.z >> 16; pk[6] = w.w & 0xffffu; pk[7] = w.w >> 16;
+            }
+            const float nm0 = __ldg(nu + m[0]);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const float nm = uni ? nm0 : __ldg(nu + m[t]);
+                const uint32_t sg = pk[t] >> (BITS - 1);
+                const float lf = (float)(int)(pk[t] & ((1u << (BITS - 1)) - 1u));
+                // (float(l) * (2 * sign - 1)) * norm / s, qsgd_compressor.py:69-70
+                const float val = __fmul_rn(__fmul_rn(__fmul_rn(lf, sg ? 1.0f : -1.0f), nm), inv_s);
+                acc[t] = (u == 0) ? val : __fadd_rn(acc[t], val);
+            }
+        }
+        float4 o[2];
+        float *of = reinterpret_cast<float *>(o);
+        if (accumulate) {
+            o[0] = reinterpret_cast<const float4 *>(out)[2 * q];
+            o[1] = reinterpret_cast<const float4 *>(out)[2 * q + 1];
+        }
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            float r = acc[t];
+            if (inv_u != 0.0f) r = __fmul_rn(r, inv_u);
+            else if (div_u != 0.0f) r = __fdiv_rn(r, div_u);
+            if (accumulate) r = (accumulate == 2) ? __fsub_rn(of[t], r) : __fadd_rn(of[t], r);
+            of[t] = r;
+        }
+        reinterpret_cast<float4 *>(out)[2 * q] = o[0];
+        reinterpret_cast<float4 *>(out)[2 * q + 1] = o[1];
     }
 }
 
@@ -647,7 +634,7 @@ int qsgd_decode_reduce(const float *norm, const void *packed, int64_t user_strid
         (user_stride & 15) == 0 && n < (1ll << 40) && n_chunks < (1ll << 31)) {
         float inv_u, div_u;
         mean_factors(mean, n_users, &inv_u, &div_u);
-        const int grid8 = grid_for((n + 255) / 256, 8, 16);
+        const int grid8 = grid_for(n8 + 1, 256, 16);
 #define GQ_D8(B, UU) GQ_CUDA(launch_pdl(qsgd_decode_reduce8_kernel<B, UU>, dim3(grid8), dim3(256), 0, st, norm, packed, user_stride, \
                                         n_users, n, chunk_start, (int)n_chunks, (uint32_t)(dim > 0 ? dim : 1), 1.0f / s, inv_u, div_u, accumulate, out))
 #define GQ_D8B(B) do { if (n_users == 1) GQ_D8(B, 1); else if (n_users == 2) GQ_D8(B, 2); else if (n_users == 4) GQ_D8(B, 4); \
