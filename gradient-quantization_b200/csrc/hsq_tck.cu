@@ -11,8 +11,9 @@
 // the last N-tile of a row tile the two groups exchange their maxima, and every coarse group whose
 // maximum lies within 2 * eps of the row maximum is rescored exactly (ascending-j fmaf chain over the
 // fp32 codebook, read through L1/L2; first index wins) -- the same exactness argument as hsq_tc.cu.
-// As in hsq_tc2.cu, the MMA of tile j + 2 is issued by the last epilogue warp to leave TMEM buffer
-// j & 1 (no issuer-warp wake-up in the buffer turnaround).
+// A dedicated warp issues the MMAs (it waits, with the low-latency mbarrier wait, for the four warps
+// of the buffer's epilogue group to release it; letting the last of them issue the next MMA itself was
+// the first design and left the buffer idle while that warp also waited for the operand tiles).
 // Bound: tensor pipe (2 * K flop per element: 32 MMAs per row tile at K = 4096) with the epilogue's
 // 16 first passes per row tile close behind.
 #include <cuda.h>
@@ -45,9 +46,9 @@ constexpr int kThreads = 128 + 256;                // 4 control warps + 2 epilog
 
 __host__ __device__ inline uint32_t cm_bytes(int K) { return (uint32_t)(K / 64) * kTileM * 16u; }
 __host__ __device__ inline uint32_t off_misc(int K) { return kOffCm + cm_bytes(K); }
-// misc region: mbarriers (afull[2] aempty[2] bfull[4] bempty[4] tfull[2]) | s_rel[2] | tmem ptr | s_amax[2][128] |
+// misc region: mbarriers (afull[2] aempty[2] bfull[4] bempty[4] tfull[2] tempty[2]) | tmem ptr | s_amax[2][128] |
 //              s_best[128] x (bits, k, u)
-constexpr uint32_t kMiscBytes = 14 * 8 + 16 + 16 + 2 * 128 * 4 + 128 * 12;
+constexpr uint32_t kMiscBytes = 16 * 8 + 16 + 16 + 2 * 128 * 4 + 128 * 12;
 __host__ __device__ inline uint32_t smem_bytes(int K) { return off_misc(K) + kMiscBytes + 1024; }
 
 // TF32-rounded copy of the codebook (row-major [K, 16]) and the largest codeword norm
@@ -124,10 +125,10 @@ hsq_search_tck_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
     const uint32_t bar_bfull = bar_aempty + 16;
     const uint32_t bar_bempty = bar_bfull + 32;
     const uint32_t bar_tfull = bar_bempty + 32;
-    uint32_t *s_rel = reinterpret_cast<uint32_t *>(misc + 14 * 8);
-    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(misc + 14 * 8 + 16);
-    float *s_amax = reinterpret_cast<float *>(misc + 14 * 8 + 32);
-    int *s_best = reinterpret_cast<int *>(misc + 14 * 8 + 32 + 2 * 128 * 4);
+    const uint32_t bar_tempty = bar_tfull + 16;
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(misc + 16 * 8 + 16);
+    float *s_amax = reinterpret_cast<float *>(misc + 16 * 8 + 32);
+    int *s_best = reinterpret_cast<int *>(misc + 16 * 8 + 32 + 2 * 128 * 4);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -143,13 +144,12 @@ hsq_search_tck_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
             mbar_init(bar_afull + 8 * i, 1);
             mbar_init(bar_aempty + 8 * i, 8);    // one arrive per epilogue warp
             mbar_init(bar_tfull + 8 * i, 1);
+            mbar_init(bar_tempty + 8 * i, 4);    // the four warps of the buffer's epilogue group
         }
         for (int i = 0; i < kBStages; ++i) {
             mbar_init(bar_bfull + 8 * i, 1);
             mbar_init(bar_bempty + 8 * i, 1);    // tcgen05.commit of the tile's MMAs
         }
-        s_rel[0] = 0u;
-        s_rel[1] = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -168,8 +168,9 @@ hsq_search_tck_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
     // MMA of pair j: A = row tile j / T (ring of 2), B = ring slot j & 3, accumulators in TMEM buffer j & 1
     auto issue_mma = [&](int j) {
         const int rtl = j / T;
-        mbar_wait(bar_afull + 8 * (rtl & 1), (rtl >> 1) & 1);
-        mbar_wait(bar_bfull + 8 * (j & 3), (j >> 2) & 1);
+        mbar_wait_sleep(bar_afull + 8 * (rtl & 1), (rtl >> 1) & 1);
+        mbar_wait_sleep(bar_bfull + 8 * (j & 3), (j >> 2) & 1);
+        if (j >= 2) mbar_wait_hw(bar_tempty + 8 * (j & 1), ((j - 2) >> 1) & 1);   // the buffer's previous pass is read out
         tc_fence_after();
         const uint64_t adesc = make_desc(smem_u32(s_a + (rtl & 1) * kATileBytes));
         const uint64_t bdesc = make_desc(smem_u32(s_b + (j & 3) * kBTileBytes));
@@ -197,9 +198,9 @@ hsq_search_tck_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
             }
         }
     } else if (warp == 1) {
-        // ---------------------------------------- first two MMAs (then: last arriver, see header) ---
+        // -------------------------------------------------------- MMA issuer ---
         if (lane == 0) {
-            for (int j = 0; j < total && j < 2; ++j) issue_mma(j);
+            for (int j = 0; j < total; ++j) issue_mma(j);
         }
     } else if (warp >= 4) {
         // ----------------------------------------------------------- epilogue ---
@@ -214,7 +215,7 @@ hsq_search_tck_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
             float amax = 0.0f;
             for (int t = e; t < T; t += 2) {
                 const int j = rtl * T + t;
-                mbar_wait(bar_tfull + 8 * e, (j >> 1) & 1);
+                mbar_wait_hw(bar_tfull + 8 * e, (j >> 1) & 1);
                 __syncwarp();
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(e * kTileN);
@@ -232,14 +233,10 @@ hsq_search_tck_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
                     cm[2 * h + 1] = absmax16(sb);
                     if (h + 1 < 8) tmem_ld_wait16(sa);
                 }
-                // release the TMEM buffer; the last of the group's four warps issues the MMA of pair j + 2
+                // release the TMEM buffer (pair j + 2 is issued by the MMA warp as soon as all four warps have)
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) {
-                    const uint32_t old = atomicAdd(s_rel + e, 1u);
-                    if ((old & 3u) == 3u && j + 2 < total) issue_mma(j + 2);
-                }
-                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_tempty + 8 * e);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     s_cm[(t * 4 + q) * kTileM + row] = make_float4(cm[4 * q], cm[4 * q + 1], cm[4 * q + 2], cm[4 * q + 3]);
