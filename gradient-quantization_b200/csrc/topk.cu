@@ -42,17 +42,31 @@ __global__ void topk_setup_kernel(const int64_t *__restrict__ seg_start, const i
 {
     pdl_launch_dependents();
     pdl_wait();
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
+    if (blockIdx.x == 0 && threadIdx.x < 32) {
+        // exclusive prefix sums of the tensors' tile / run counts: one warp, 32 tensors per step
+        const int lane = threadIdx.x;
         int64_t acc = 0, racc = 0;
-        for (int s = 0; s < n_seg; ++s) {
-            tile_prefix[s] = acc;
-            run_prefix[s] = racc;
-            const int64_t tiles = (seg_start[s + 1] - seg_start[s] + kTile - 1) / kTile;
-            acc += tiles;
-            racc += (tiles + kSuper - 1) / kSuper;
+        for (int s0 = 0; s0 < n_seg; s0 += 32) {
+            const int s = s0 + lane;
+            const int64_t tiles = s < n_seg ? (seg_start[s + 1] - seg_start[s] + kTile - 1) / kTile : 0;
+            const int64_t runs = (tiles + kSuper - 1) / kSuper;
+            int64_t it = tiles, ir = runs;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int64_t yt = __shfl_up_sync(0xffffffffu, it, o), yr = __shfl_up_sync(0xffffffffu, ir, o);
+                if (lane >= o) { it += yt; ir += yr; }
+            }
+            if (s < n_seg) {
+                tile_prefix[s] = acc + it - tiles;
+                run_prefix[s] = racc + ir - runs;
+            }
+            acc += __shfl_sync(0xffffffffu, it, 31);
+            racc += __shfl_sync(0xffffffffu, ir, 31);
         }
-        tile_prefix[n_seg] = acc;
-        run_prefix[n_seg] = racc;
+        if (lane == 0) {
+            tile_prefix[n_seg] = acc;
+            run_prefix[n_seg] = racc;
+        }
     }
     const int64_t nh = (int64_t)n_seg * kBins;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nh; i += (int64_t)gridDim.x * blockDim.x)
@@ -482,7 +496,8 @@ int topk_select(const float *grad, int64_t n, const int64_t *seg_start, const in
     const int64_t max_runs = n / (kTile * kSuper) + n_seg + 1;
     const int grid_runs = (int)(max_runs < cap ? max_runs : cap);
     const int64_t warp_blocks = (max_tiles + 7) / 8;
-    const int grid_lists = (int)(warp_blocks < cap ? warp_blocks : cap);
+    // (one warp per tile, a chain of dependent loads per tile: as many warps in flight as fit)
+    const int grid_lists = (int)(warp_blocks < 2 * cap ? warp_blocks : 2 * cap);
     const int grid_setup = (int)std::min<int64_t>(((int64_t)n_seg * kBins + 255) / 256, cap);
     GQ_CUDA(launch_pdl(topk_setup_kernel, dim3(grid_setup), dim3(256), 0, st, seg_start, k, n_seg, w.tile_prefix,
                        w.run_prefix, w.state, w.hist));

@@ -27,3 +27,21 @@ def ring_send_next(records, rank, world):
 def ring_broadcast_last(records, world):
     """ring: the last hop's record is what every rank decodes (ring_quantizer.py:45-49)."""
     dist.broadcast(records[world - 1], src=world - 1)
+
+
+def _part_ops(op, record, ranges, peer):
+    return [dist.P2POp(op, record[a:b], peer) for a, b in ranges if b > a]
+
+
+def ring_receive_previous_part(records, rank, ranges):
+    """Pipelined ring: one stage's byte ranges of the previous hop's record, as ONE batched group of
+    receives (the sections of a stage are not contiguous in the record)."""
+    if rank > 0:
+        for w in dist.batch_isend_irecv(_part_ops(dist.irecv, records[rank - 1], ranges, rank - 1)):
+            w.wait()
+
+
+def ring_send_next_part(records, rank, world, ranges):
+    if rank + 1 < world:
+        for w in dist.batch_isend_irecv(_part_ops(dist.isend, records[rank], ranges, rank + 1)):
+            w.wait()

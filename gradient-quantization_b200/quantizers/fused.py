@@ -197,6 +197,71 @@ class FusedPlan:
         self.record_bytes = _up(rec)
         self.workspace_bytes = ws
 
+    # --------------------------------------------------------------- parts ---
+    def make_parts(self, n_parts):
+        """Cut the plan into n_parts stages for the pipelined ring (the chain is per tensor, so
+        rank r can work on one group of tensors while rank r + 1 works on the previous one).  Every HSQ
+        group is cut at tensor boundaries into contiguous sub-ranges of about equal chunk counts (cuts
+        only where the chunk offset is a multiple of 16, so that every section of a part stays 16-byte
+        aligned); all other groups (and the identity tensors) belong to part 0.  Returns the number of
+        parts actually made.  encode(part=p) / decode(part=p) / part_byte_ranges(p) then address one part."""
+        n_parts = max(1, int(n_parts))
+        for g in self.groups:
+            g.part_cuts = None
+            if g.kind != "hsq" or n_parts == 1 or g.n_bit == 32:
+                continue
+            starts = g.seg_start_host
+            cuts = [0]
+            for k in range(1, n_parts):
+                target = g.n_chunks * k // n_parts
+                # first tensor boundary at or after the target whose chunk offset is 16-aligned
+                t = next((i for i in range(cuts[-1] + 1, g.n_seg) if starts[i] >= target and starts[i] % 16 == 0), None)
+                if t is None:
+                    break
+                cuts.append(t)
+            cuts.append(g.n_seg)
+            if len(cuts) > 2:
+                g.part_cuts = cuts
+                g.part_seg = [torch.tensor([x - starts[cuts[k]] for x in starts[cuts[k]:cuts[k + 1] + 1]],
+                                           dtype=torch.int64, device=self.device) for k in range(len(cuts) - 1)]
+        self.n_parts = max([len(g.part_cuts) - 1 for g in self.groups if getattr(g, "part_cuts", None)] or [1])
+        return self.n_parts
+
+    def _part_range(self, g, part):
+        """(first tensor, last tensor + 1, first chunk, last chunk + 1) of HSQ group g in `part`, or None."""
+        cuts = getattr(g, "part_cuts", None)
+        if cuts is None:
+            return (0, g.n_seg, 0, g.n_chunks) if part == 0 else None
+        if part >= len(cuts) - 1:
+            return None
+        ta, tb = cuts[part], cuts[part + 1]
+        return ta, tb, g.seg_start_host[ta], g.seg_start_host[tb]
+
+    def part_byte_ranges(self, part):
+        """Byte ranges [(begin, end)] of one packed record that `part` produces (what travels per hop)."""
+        out = []
+        for g in self.groups:
+            if g.kind == "hsq" and getattr(g, "part_cuts", None) is not None:
+                r = self._part_range(g, part)
+                if r is None:
+                    continue
+                ta, tb, ca, cb = r
+                out.append((g.codes_off + ca * g.code_bytes, g.codes_off + cb * g.code_bytes))
+                out.append((g.l_off + ca * g.l_bytes, g.l_off + cb * g.l_bytes))
+                out.append((g.lbub_off + 8 * ta, g.lbub_off + 8 * tb))
+            elif part == 0:
+                if g.kind == "hsq":
+                    out.append((g.codes_off, g.lbub_off + _up(g.n_seg * 8)))
+                elif g.kind == "qsgd":
+                    out.append((g.norm_off, g.packed_off + _up((g.n + 3) // 4 * 4 * g.bits // 8)))
+                elif g.kind == "sign":
+                    out.append((g.packed_off, g.packed_off + _up((g.n + 3) // 4)))
+                elif g.kind == "topk":
+                    out.append((g.idx_off, g.val_off + _up(g.k_total * 4)))
+                elif g.kind == "identity" and g.n:
+                    out.append((g.raw_off, g.raw_off + _up(g.n * 4)))
+        return out
+
     # --------------------------------------------------------------- views ---
     def view(self, i, buf=None):
         """View of tensor i inside the arena (or another buffer laid out like it)."""
@@ -292,7 +357,7 @@ class FusedPlan:
         return out, pos
 
     # --------------------------------------------------------------- encode ---
-    def encode(self, user, src=None, uniforms=None, rng_user=None, shared_rng=False):
+    def encode(self, user, src=None, uniforms=None, rng_user=None, shared_rng=False, part=None):
         """Compress the arena (or `src`, laid out like it) into records[user].
         rng_user: logical user whose Philox stream the stochastic rounding draws from (default: the
         record row); shared_rng: the rank-independent stream instead (second phase of --two-phase).
@@ -307,9 +372,34 @@ class FusedPlan:
         st = _lib.stream()
         base = rec.data_ptr()
         ident, carrier = self._rider_pair()
+        if part is not None and not hasattr(self, "n_parts"):
+            raise _lib.GQError("encode(part=...) needs make_parts() first")
         for g in self.groups:
             gp = src_ptr + g.arena_off * 4
             r = None if uniforms is None else uniforms.get(id(g))
+            if part is not None:
+                if g.kind == "hsq" and getattr(g, "part_cuts", None) is not None:
+                    pr = self._part_range(g, part)
+                    if pr is None:
+                        continue
+                    ta, tb, ca, cb = pr
+                    if g is carrier and part == 0:
+                        _lib.call("gq_attach_f32_reduce", src_ptr + ident.arena_off * 4, 0, None, 1, ident.n, 0, 0,
+                                  base + ident.raw_off)
+                    # the same Philox indices as the whole-group call: chunk i of the group draws element offset + i
+                    if part == 0:
+                        n_rand = g.n_chunks if self.random else 0
+                        g._part_rng = take(n_rand) if (n_rand and r is None) else (0, 0)
+                    seed, off = g._part_rng
+                    _lib.call("gq_hsq_encode", gp + ca * g.dim * 4, cb - ca, g.dim, _lib.ptr(g.codebook), g.K,
+                              _lib.ptr(g.part_seg[part]), tb - ta, g.n_bit, self.random,
+                              None if r is None else r.data_ptr() + ca * 4, seed, off + (ca if r is None else 0),
+                              base + g.codes_off + ca * g.code_bytes, g.code_bytes, base + g.l_off + ca * g.l_bytes,
+                              g.l_bytes, base + g.lbub_off + 8 * ta, self.u_scratch.data_ptr() + ca * 4,
+                              _lib.ptr(self.workspace), self.workspace.numel(), self.algo, st)
+                    continue
+                if part != 0:
+                    continue
             if g is carrier:   # out = the raw fp32 tensors, copied into the record by the next call
                 _lib.call("gq_attach_f32_reduce", src_ptr + ident.arena_off * 4, 0, None, 1, ident.n, 0, 0,
                           base + ident.raw_off)
@@ -381,7 +471,7 @@ class FusedPlan:
         return all(g.kind != "topk" for g in self.groups)
 
     def decode(self, first_user=0, n_users=None, mean=True, accumulate=False, out=None,
-               base_ptr=None, user_offsets=None):
+               base_ptr=None, user_offsets=None, part=None):
         """out (arena layout) = [out +] reduce over records[first_user : first_user+n_users].
         base_ptr / user_offsets (ctypes int64 array): user 0's record address and every user's byte
         offset from it, for records that live in different buffers (peer-to-peer exchange)."""
@@ -410,6 +500,22 @@ class FusedPlan:
         stride = self.record_bytes
         for g in self.groups:
             op = out.data_ptr() + g.arena_off * 4
+            if part is not None:
+                if g.kind == "hsq" and getattr(g, "part_cuts", None) is not None:
+                    pr = self._part_range(g, part)
+                    if pr is None:
+                        continue
+                    ta, tb, ca, cb = pr
+                    if g is carrier and part == 0:
+                        _lib.call("gq_attach_f32_reduce", base + ident.raw_off, stride, None, n_users, ident.n, mean, acc,
+                                  out.data_ptr() + ident.arena_off * 4)
+                    _lib.call("gq_hsq_decode_reduce", base + g.codes_off + ca * g.code_bytes, g.code_bytes,
+                              base + g.l_off + ca * g.l_bytes, g.l_bytes, base + g.lbub_off + 8 * ta, None, stride,
+                              n_users, cb - ca, g.dim, _lib.ptr(g.codebook), g.K, _lib.ptr(g.part_seg[part]), tb - ta,
+                              g.n_bit, mean, acc, op + ca * g.dim * 4, st)
+                    continue
+                if part != 0:
+                    continue
             if g is carrier:
                 _lib.call("gq_attach_f32_reduce", base + ident.raw_off, stride, None, n_users, ident.n, mean, acc,
                           out.data_ptr() + ident.arena_off * 4)

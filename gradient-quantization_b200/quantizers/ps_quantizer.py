@@ -1,4 +1,5 @@
 import os
+import sys
 
 import torch
 
@@ -80,7 +81,7 @@ class PSQuantizer(QuantizerBase):
         elif p2p is not None:
             p2p.close()
         if self.rank == 0:
-            print("gq_b200: ps exchange = %s" % self.exchange_name(), flush=True)
+            print("gq_b200: ps exchange = %s" % self.exchange_name(), file=sys.stderr, flush=True)   # stdout stays clean for callers that parse it
 
     def exchange_name(self):
         if self.p2p is None:

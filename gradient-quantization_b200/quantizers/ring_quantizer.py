@@ -19,6 +19,18 @@ class RingQuantizer(QuantizerBase):
 
     def __init__(self, Compressor, parameters, args):
         super().__init__(Compressor, parameters, args)
+        # Pipelined chain: the chain is per tensor, so the plan is cut into stages and rank r
+        # works on stage s while rank r + 1 works on stage s - 1: all ranks are busy after U - 1 stages.
+        # args.ring_parts / GQ_RING_PARTS; default 4 stages from three ranks on, 2 for two ranks.
+        import os
+        self.parts = 1
+        if self.plan is not None and not self.error_feedback:
+            want = getattr(args, "ring_parts", None)
+            if want is None:
+                want = os.environ.get("GQ_RING_PARTS")
+            if want is None:
+                want = (4 if self.world >= 3 else 2) if self.distributed else 1
+            self.parts = self.plan.make_parts(int(want))
 
     def record(self, user, epoch, uniforms=None):
         scale = feedback_scale(self.args, epoch)
@@ -28,6 +40,8 @@ class RingQuantizer(QuantizerBase):
         if self.distributed and user != self.rank:
             raise _lib.GQError("distributed mode: rank %d records user %d only" % (self.rank, self.rank))
         plan.gather(self._grads())
+        if self.parts > 1:
+            return self._chain_parts(user, plan.arena, uniforms)
         if user != 0:
             if self.distributed:
                 xch.ring_receive_previous(plan.records, user)
@@ -56,6 +70,20 @@ class RingQuantizer(QuantizerBase):
         if self.distributed:
             xch.ring_send_next(plan.records, user, self.world)
 
+    def _chain_parts(self, user, buf, uniforms=None):
+        """This user's hop of the chain, stage by stage: receive the stage of the previous hop's record,
+        add its decode to the local gradient, encode the sum, send the stage on."""
+        plan = self.plan
+        for p in range(self.parts):
+            ranges = plan.part_byte_ranges(p)
+            if user != 0:
+                if self.distributed:
+                    xch.ring_receive_previous_part(plan.records, user, ranges)
+                plan.decode(first_user=user - 1, n_users=1, mean=False, accumulate=True, out=buf, part=p)
+            plan.encode(user, src=buf, uniforms=uniforms, rng_user=user, part=p)
+            if self.distributed:
+                xch.ring_send_next_part(plan.records, user, self.world, ranges)
+
     def step_buffers(self, src, out):
         """One ring step on raw arena-shaped device buffers (bench.py): this rank's hop -- receive the
         previous hop's record, add its decode to the local gradient IN PLACE (ring_quantizer.py:31-32
@@ -64,6 +92,9 @@ class RingQuantizer(QuantizerBase):
         plan = self.plan
         users = [self.rank] if self.distributed else range(self.args.num_users)
         for user in users:
+            if self.parts > 1:
+                self._chain_parts(user, src)
+                continue
             if user != 0:
                 if self.distributed:
                     xch.ring_receive_previous(plan.records, user)
@@ -78,14 +109,22 @@ class RingQuantizer(QuantizerBase):
 
     def launches_per_step(self):
         """My kernel launches per rank and step: (decode-accumulate +) encode + final decode."""
-        n = self.plan.launches_per_encode() + self.plan.launches_per_decode(1)
+        # every extra stage of the pipelined chain adds one encode (and one decode-accumulate) launch per
+        # partitioned group
+        extra = (self.parts - 1) * sum(1 for g in self.plan.groups if getattr(g, "part_cuts", None))
+        enc = self.plan.launches_per_encode() + extra
+        dec = self.plan.launches_per_decode(1)
         if self.distributed:
-            return n + (self.plan.launches_per_decode(1) if self.rank > 0 else 0)
+            return enc + dec + ((dec + extra) if self.rank > 0 else 0)
         u = self.args.num_users
-        return u * self.plan.launches_per_encode() + u * self.plan.launches_per_decode(1)
+        return u * enc + (u - 1) * (dec + extra) + dec
 
     def exchange_name(self):
-        return "NCCL send/recv chain + broadcast" if self.distributed else "none"
+        if not self.distributed:
+            return "none"
+        if self.parts > 1:
+            return "NCCL batched send/recv chain pipelined over %d stages of tensors + broadcast" % self.parts
+        return "NCCL send/recv chain + broadcast"
 
     def _record_per_parameter(self, user, scale):
         for i, param in enumerate(self.parameters):

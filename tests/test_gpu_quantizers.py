@@ -174,3 +174,12 @@ def test_nan_gradient_makes_the_whole_tensor_nan(algo):
     q.apply()
     assert torch.isnan(params[0].grad).all()
     assert torch.isfinite(params[1].grad).all()
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names("ring_") if "ef" not in n])
+def test_ring_in_stages_equals_the_reference_golden(name, monkeypatch):
+    """The pipelined ring cuts the plan into stages of tensors; hop by hop and stage by
+    stage it must reproduce the reference's chain bit for bit (same Philox / uniform indices)."""
+    monkeypatch.setenv("GQ_RING_PARTS", "3")
+    g = golden(name)
+    _run(g, fused=True)
