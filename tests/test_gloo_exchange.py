@@ -52,8 +52,26 @@ def _worker(rank, world, port, out_dir):
     xch.ring_send_next(plan.records, rank, world)
     xch.ring_broadcast_last(plan.records, world)
     last_ok = np.array_equal(plan.records[world - 1].numpy(), np.full(rb, 10 + world - 1, np.uint8))
+    # pipelined ring: the plan cut into stages; every stage's byte ranges travel as one batched group and
+    # together the stages cover every useful byte of the record exactly once
+    n_parts = plan.make_parts(3)
+    plan.records.zero_()
+    covered = np.zeros(rb, dtype=np.int32)
+    stage_ok = n_parts >= 2
+    for p in range(n_parts):
+        ranges = plan.part_byte_ranges(p)
+        for a, b in ranges:
+            covered[a:b] += 1
+        xch.ring_receive_previous_part(plan.records, rank, ranges)
+        if rank > 0:
+            for a, b in ranges:
+                stage_ok = stage_ok and bool((plan.records[rank - 1][a:b] == 20 + p).all())
+        for a, b in ranges:
+            plan.records[rank][a:b] = 20 + p
+        xch.ring_send_next_part(plan.records, rank, world, ranges)
+    stage_ok = stage_ok and covered.max() == 1 and int((covered == 1).sum()) >= plan.wire_bytes()
     with open(os.path.join(out_dir, "rank%d.txt" % rank), "w") as fh:
-        fh.write("%d %d %d" % (ok_ps, prev_ok, last_ok))
+        fh.write("%d %d %d %d" % (ok_ps, prev_ok, last_ok, stage_ok))
     dist.destroy_process_group()
 
 
@@ -63,7 +81,7 @@ def test_ps_and_ring_exchange_gloo_world2(tmp_path):
                        start_method="spawn")
     for r in range(world):
         flags = open(tmp_path / ("rank%d.txt" % r)).read().split()
-        assert flags == ["1", "1", "1"], (r, flags)
+        assert flags == ["1", "1", "1", "1"], (r, flags)
 
 
 def test_distributed_quantizer_requires_one_user_per_rank():
