@@ -659,7 +659,7 @@ def main():
     if getattr(q, "p2p", None) is not None:
         exch = "peer-to-peer (%s): packed records cross NVLink through peer-mapped memory" % q.exchange_name()
     elif world > 1:
-        exch = "NCCL (%s)" % ("all-gather of packed records" if a.mode == "ps" else "send/recv chain + broadcast of packed records")
+        exch = "NCCL (%s)" % ("all-gather of packed records" if a.mode == "ps" else q.exchange_name() + ", packed records")
     else:
         exch = "none (1 user)"
     line = {

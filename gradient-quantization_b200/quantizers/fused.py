@@ -111,6 +111,14 @@ class FusedPlan:
                 raise _lib.GQError("fused plan does not support %r" % (self.Compressor,))
             g.add(i, size)
             self.tensor_group.append(g)
+        # HSQ groups: tensors whose chunk count is a multiple of 16 first (model order otherwise), so that
+        # every tensor boundary among them is a 16-byte boundary of the code / level sections and the ring's
+        # stages (make_parts) can be cut there -- ResNet-50's first convolution (108 chunks) would otherwise
+        # misalign every later boundary
+        for (kind, key), g in by_key.items():
+            if kind == "hsq":
+                pairs = sorted(zip(g.tensors, g.sizes), key=lambda p: (p[1] // key[0]) % 16 != 0)
+                g.tensors, g.sizes = [p[0] for p in pairs], [p[1] for p in pairs]
         # identity last, compressed groups in first-appearance order
         self.groups = [by_key[k] for k in order if k[0] != "identity"]
         self.groups += [by_key[k] for k in order if k[0] == "identity"]
@@ -334,7 +342,7 @@ class FusedPlan:
         """Cut a flat uniform stream drawn in the reference's call order (tensor by
         tensor: rand(N/d) per HSQ tensor, rand(size) per QSGD tensor; tensors in
         `skip` consume nothing) into one device array per group."""
-        per_group = {id(g): [] for g in self.groups}
+        per_group = {id(g): {} for g in self.groups}
         pos = 0
         for i, g in enumerate(self.tensor_group):
             if g.kind == "hsq":
@@ -349,11 +357,11 @@ class FusedPlan:
                 chunk = torch.as_tensor(stream[pos:pos + n], dtype=torch.float32)
                 assert chunk.numel() == n, "uniform stream exhausted"
                 pos += n
-            per_group[id(g)].append(chunk)
+            per_group[id(g)][i] = chunk
         out = {}
         for g in self.groups:
-            if per_group[id(g)]:
-                out[id(g)] = torch.cat(per_group[id(g)]).to(self.device)
+            if per_group[id(g)]:       # in the group's own tensor order (HSQ groups are not in model order)
+                out[id(g)] = torch.cat([per_group[id(g)][i] for i in g.tensors]).to(self.device)
         return out, pos
 
     # --------------------------------------------------------------- encode ---

@@ -131,6 +131,31 @@ class PeerRecords:
         _lib.call("gq_attach_remote_record", len(deltas), mc, (ctypes.c_int64 * len(deltas))(*deltas), ident_ptr,
                   ident_bytes, ctypes.cast(flags, ctypes.c_void_p), self.world, self.epoch)
 
+    def attach_delivery_to(self, plan, targets, epoch, with_ident=True):
+        """Ring hop: the next encode of `plan` into row `row()` also stores what it writes into the same
+        row of the blocks of `targets` (all other ranks: once through the multicast mapping when there
+        is one) and then writes `epoch` into this rank's word of those ranks' flag arrays."""
+        local = self._addr(self.rank, self.rank)
+        everyone = len(targets) == self.world - 1
+        if everyone and self.mc_base and self.world > 2:
+            deltas = [self.mc_base + self.row() * self.record_bytes - local]
+            mc = 1
+            flag_ranks = list(range(self.world))
+        else:
+            deltas = [self._addr(r, self.rank) - local for r in targets]
+            mc = 0
+            flag_ranks = list(targets)
+        ident = next((g for g in plan.groups if g.kind == "identity" and g.n), None) if with_ident else None
+        ident_ptr = local + ident.raw_off if ident is not None else None
+        ident_bytes = (ident.n * 4 + 15) // 16 * 16 if ident is not None else 0
+        flags = (ctypes.c_void_p * len(flag_ranks))(*[int(self._flag_ptrs[r]) + 4 * self.rank for r in flag_ranks])
+        _lib.call("gq_attach_remote_record", len(deltas), mc, (ctypes.c_int64 * len(deltas))(*deltas), ident_ptr,
+                  ident_bytes, ctypes.cast(flags, ctypes.c_void_p), len(flag_ranks), int(epoch))
+
+    def attach_wait_for(self, src_rank, epoch):
+        """Ring hop, receiving side: the next decode waits until `src_rank` has announced `epoch` here."""
+        _lib.call("gq_attach_peer_wait", int(self._flag_ptrs[self.rank]) + 4 * src_rank, 1, int(epoch))
+
     def attach_wait(self):
         """Fused push, receiving side: the next decode waits for every rank's flag of this epoch."""
         _lib.call("gq_attach_peer_wait", int(self._flag_ptrs[self.rank]), self.world, self.epoch)

@@ -28,9 +28,15 @@ dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 
 shapes = FCN_SHAPES + [(64, 3, 3, 3)]
+cases = (("ps", "hsq"), ("ring", "hsq"), ("ps", "qsgd"), ("ps", "sign"), ("ps", "topk"), ("ring", "qsgd"))
+if os.environ.get("GQ_DIST_SHAPES") == "resnet50":      # the headline workload (the staged ring cuts it into parts)
+    from util import resnet50_shapes
+    shapes = resnet50_shapes()
+if os.environ.get("GQ_DIST_CASES"):                     # e.g. "ring:hsq,ps:hsq"
+    cases = tuple(tuple(c.split(":")) for c in os.environ["GQ_DIST_CASES"].split(","))
 sizes = [int(np.prod(s)) for s in shapes]
 fails = 0
-for mode, quant in (("ps", "hsq"), ("ring", "hsq"), ("ps", "qsgd"), ("ps", "sign"), ("ps", "topk"), ("ring", "qsgd")):
+for mode, quant in cases:
     a = make_args(mode=mode, num_users=world, c_dim=16 if quant == "hsq" else 128,
                   n_bit=6 if quant == "hsq" else 2, cr=100)
     Comp = {"hsq": gq_b200.NearestNeighborCompressor, "qsgd": gq_b200.QSGDCompressor,
@@ -71,7 +77,7 @@ for mode, quant in (("ps", "hsq"), ("ring", "hsq"), ("ps", "qsgd"), ("ps", "sign
     flag = torch.tensor([0 if ok else 1], device=dev)
     dist.all_reduce(flag)
     if rank == 0:
-        print("%-4s %-5s world=%d: %s" % (mode, quant, world, "OK (bit-exact on every rank)" if flag.item() == 0 else "MISMATCH"), flush=True)
+        print("%-4s %-5s world=%d [%s]: %s" % (mode, quant, world, q.exchange_name()[:60], "OK (bit-exact on every rank)" if flag.item() == 0 else "MISMATCH"), flush=True)
     fails += int(flag.item())
 dist.barrier()
 dist.destroy_process_group()

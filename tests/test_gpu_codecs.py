@@ -61,6 +61,41 @@ def test_qsgd_packed_wire_roundtrip(c_dim, n_bit):
         assert np.array_equal(plan.view(i, out).cpu().numpy().reshape(-1), ref), i
 
 
+@pytest.mark.parametrize("c_dim,n_bit,shapes", [
+    (8, 2, [(64, 128), (100,), (32, 64), (3, 2048)]),          # 8 lanes per chunk
+    (32, 4, [(64, 128), (100,), (32, 64), (3, 2048)]),
+    (512, 2, [(64, 128), (100,), (32, 64), (3, 2048)]),        # 4 float4 per lane
+    (2048, 6, [(64, 128), (100,), (32, 64), (3, 2048)]),       # 16 float4 per lane
+    (4096, 2, [(64, 128), (100,), (2, 4096)]),                 # beyond the register-resident kernel: generic path
+    (50, 2, [(30, 100), (7,), (25, 80)]),                      # chunk dim not a multiple of 4: generic path
+    (100, 8, [(30, 100), (7,), (25, 80)]),                     # 25 float4 per chunk (one lane group, partly idle)
+])
+def test_qsgd_every_chunk_layout_against_the_oracle(c_dim, n_bit, shapes):
+    """Every instantiation of the one-launch QSGD encode (lanes per chunk, float4 per lane) and the generic
+    fallbacks, through the packed record and the fused decode, bit for bit against the oracle."""
+    from gq_b200.quantizers.fused import FusedPlan
+    U = 2
+    a = make_args(c_dim=c_dim, n_bit=n_bit, num_users=U)
+    plan = FusedPlan(gq_b200.QSGDCompressor, shapes, a, torch.device(DEV), U)
+    sizes = [int(np.prod(s)) for s in shapes]
+    codecs = [O.QSGD(n, s, c_dim, n_bit, True) if n > 1000 else O.Identity() for n, s in zip(sizes, shapes)]
+    n_draws = sum(n for n in sizes if n > 1000)
+    decs = []
+    for u in range(U):
+        xs = [gen_input(900 + 10 * u + i, n).reshape(s) for i, (n, s) in enumerate(zip(sizes, shapes))]
+        xs[0].reshape(-1)[: max(c_dim, 8)] = 0.0                      # an all-zero chunk: 0 / 0 levels
+        stream = torch_uniform_stream(170 + u, n_draws)
+        parts, used = plan.split_uniform_stream(stream)
+        plan.gather([_t(x) for x in xs])
+        plan.encode(u, uniforms=parts)
+        st = O.UniformStream(stream)
+        decs.append([c.decompress(c.compress(x, st)) for c, x in zip(codecs, xs)])
+    out = plan.decode(mean=True)
+    for i in range(len(shapes)):
+        ref = O.ps_mean(np.stack([decs[u][i].reshape(-1) for u in range(U)]))
+        assert np.array_equal(plan.view(i, out).cpu().numpy().reshape(-1), ref), i
+
+
 def test_qsgd_max_element_decodes_exactly():
     a = make_args(c_dim=128, n_bit=2)
     x = gen_input(2, 128 * 50)

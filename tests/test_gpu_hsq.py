@@ -59,9 +59,11 @@ def test_hsq_search_vs_oracle(d, K, kind):
         assert np.array_equal(u.cpu().numpy(), ou), (d, K, algo)
 
 
-def test_hsq_adversarial_ties_and_specials():
-    """Exact ties (first index wins), zero chunks, codeword inputs, huge/tiny magnitudes."""
-    d, K = 16, 256
+@pytest.mark.parametrize("d", [16, 8, 32])
+def test_hsq_adversarial_ties_and_specials(d):
+    """Exact ties (first index wins), zero chunks, codeword inputs, huge/tiny magnitudes -- at every
+    chunk dimension the tcgen05 encode handles."""
+    K = 256
     cb = codebook(d, K)
     rows = []
     rows.append(np.zeros(d, np.float32))                              # all scores 0 -> code 0
@@ -88,7 +90,7 @@ def test_hsq_adversarial_ties_and_specials():
     x = np.stack(rows * 8).astype(np.float32)
     oc, ou = O.hsq_search(x, cb)
     for algo in (_lib.ALGO_EXACT, _lib.ALGO_AUTO):
-        a = make_args(n_bit=32, hsq_algo=algo)
+        a = make_args(c_dim=d, n_bit=32, hsq_algo=algo)
         c = gq_b200.NearestNeighborCompressor(x.size, torch.Size(x.shape), a)
         u, codes = c.compress(_t(x))
         assert np.array_equal(codes.cpu().numpy().astype(np.int32), oc), algo

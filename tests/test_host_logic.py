@@ -166,3 +166,25 @@ def test_codebook_generator_small(tmp_path):
     assert len(out) == 1 and out[0].endswith("angular_dim_4_Ks_8.fvecs")
     assert fvecs_read(out[0]).shape == (8, 4)
     assert G.generate(dims=[4], Ks=[8], out_dir=str(tmp_path), train_size=500, iter=3) == []   # kept, not appended to
+
+
+def test_ring_stages_cut_the_resnet50_plan_at_aligned_tensor_boundaries():
+    """make_parts on the headline workload: the first convolution has 108 chunks, so the plan places it
+    after the tensors whose chunk count is a multiple of 16 and four real stages come out."""
+    plan = FusedPlan(gq_b200.NearestNeighborCompressor, resnet50_shapes(), make_args(), torch.device("cpu"), 2)
+    assert plan.make_parts(4) == 4
+    g = plan.groups[0]
+    covered = 0
+    for p in range(4):
+        ta, tb, ca, cb = plan._part_range(g, p)
+        assert ca % 16 == 0 and ca == covered and tb > ta
+        assert 0.15 * g.n_chunks < cb - ca < 0.40 * g.n_chunks        # about a quarter each
+        covered = cb
+    assert covered == g.n_chunks
+    # the ranges of all stages tile the codes / levels / lb-ub sections of the record exactly once
+    seen = np.zeros(plan.record_bytes, np.int32)
+    for p in range(4):
+        for b, e in plan.part_byte_ranges(p):
+            seen[b:e] += 1
+    for off, n in ((g.codes_off, g.n_chunks), (g.l_off, g.n_chunks), (g.lbub_off, 8 * g.n_seg)):
+        assert (seen[off:off + n] == 1).all()
