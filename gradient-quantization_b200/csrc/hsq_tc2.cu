@@ -112,7 +112,6 @@ struct Enc2 {
     float s;
     int random;
     Remote remote;
-    int wait_hw;                 // bit 0: epilogue, bit 1: MMA warp use the low-latency mbarrier wait
     long long *trace;            // TRACE builds only
 };
 
@@ -155,6 +154,15 @@ __device__ __forceinline__ float fma_sat(float a, float b, float c)
     return r;
 }
 __device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+// doubled maximum of |score| over a group of four codewords from its accumulators (p_a, m_a, p_b, m_b):
+// max(|p_a| + |m_a|, |p_b| + |m_b|).  (With the B rows ordered p_a, p_b, m_a, m_b one packed FADD2 with |.|
+// modifiers serves both pairs -- 64 fewer instructions per row, and measured 2.5 - 4 us SLOWER per launch:
+// the first pass is bound by the TMEM read-back, not by issue slots, and FADD2 is no cheaper than two FADDs.)
+__device__ __forceinline__ float pair_group_max(uint32_t pa, uint32_t ma, uint32_t pb, uint32_t mb)
+{
+    return fmaxf(__fadd_rn(fabsf(__uint_as_float(pa)), fabsf(__uint_as_float(ma))),
+                 __fadd_rn(fabsf(__uint_as_float(pb)), fabsf(__uint_as_float(mb))));
+}
 
 // store 4 bytes / 16 bytes at a local record address and at every remote copy of it
 __device__ __forceinline__ void remote_st32(const Remote &R, void *local, uint32_t v)
@@ -384,6 +392,7 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
         //  ~1500 cycles under contention with the other groups' rescoring, and an MMA running against the
         //  other group's TMEM loads costs them more than the early issue gains; tests/tc2_trace.py.)
         if (lane == 0) {
+            const uint64_t bdesc = make_desc_d<D>(smem_u32(s_cb));
             for (int it = 0; it < my_tiles; ++it) {
                 const int s = it % kStages;
                 const int b = it & 1;
@@ -391,14 +400,22 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
                 // so that nothing but the issue itself follows the release of the TMEM buffer
                 mbar_wait_sleep(bar_full + 8 * s, (it / kStages) & 1);
                 GQ_TRACE(12, it);
-                if (it >= 2) {
-                    if (P.wait_hw & 2) mbar_wait_hw(bar_tempty + 8 * ((it - 2) % kStages), ((it - 2) / kStages) & 1);
-                    else mbar_wait_sleep(bar_tempty + 8 * ((it - 2) % kStages), ((it - 2) / kStages) & 1);
-                }
+                // everything the issue needs is in registers BEFORE the wait for the TMEM buffer (the empty
+                // asm pins it there): this single thread competes with three busy warps for its scheduler,
+                // and every instruction between the release and the MMA is on the kernel's critical chain
+                uint64_t adesc = make_desc_d<D>(smem_u32(s_a + s * kTileBytes));
+                uint64_t bd = bdesc;
+                uint32_t taddr = tmem_base + (uint32_t)(b * kK);
+                uint32_t tfull = bar_tfull + 8 * s;
+                asm volatile("" : "+l"(adesc), "+l"(bd), "+r"(taddr), "+r"(tfull));
+                // (plain try_wait; the suspend-hint form and a test_wait spin measured the same, GQ_TC2_WAIT A/B)
+                if (it >= 2) mbar_wait_hw(bar_tempty + 8 * ((it - 2) % kStages), ((it - 2) / kStages) & 1);
                 GQ_TRACE(13, it);
                 tc_fence_after();
-                issue_tile_mma<D>(smem_u32(s_a + s * kTileBytes), smem_u32(s_cb), tmem_base + (uint32_t)(b * kK),
-                                  bar_tfull + 8 * s);
+#pragma unroll
+                for (int ks = 0; ks < D / 8; ++ks)
+                    mma_tf32(taddr, adesc + 2 * ks, bd + 2 * ks, ks ? 1u : 0u, kIdesc);
+                mma_commit(tfull);
                 GQ_TRACE(1, it);
             }
         }
@@ -462,9 +479,10 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
             const int b = it & 1;
             const int c = (tile0 + it) * kTileM + row;
             const bool valid = c < n_chunks;
-            mbar_wait_sleep(bar_full + 8 * s, ph);    // TMA data visible to this thread
-            if (P.wait_hw & 1) mbar_wait_hw(bar_tfull + 8 * s, ph);   // accumulators complete
-            else mbar_wait_sleep(bar_tfull + 8 * s, ph);
+            // (TMEM address in a register before the waits: nothing but the loads follows the commit)
+            uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * kK);
+            asm volatile("" : "+r"(taddr));
+            mbar_wait_hw(bar_tfull + 8 * s, ph);   // accumulators complete
             __syncwarp();
             tc_fence_after();
             const bool tracer = TRACE && quad == 0 && lane == 0;
@@ -473,7 +491,6 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
             // ---- pass over the 256 approximate scores of this row: maximum per group of 4 codewords
             //      (PAIR: doubled values, |p| + |m| per codeword pair)
             float gm[kNumGroups];
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * kK);
             {
                 uint32_t sa[16], sb[16];
                 tmem_ld16(taddr, sa);
@@ -484,9 +501,7 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         if (PAIR) {
-                            const float x0 = __fadd_rn(fabsf(__uint_as_float(sa[4 * g])), fabsf(__uint_as_float(sa[4 * g + 1])));
-                            const float x1 = __fadd_rn(fabsf(__uint_as_float(sa[4 * g + 2])), fabsf(__uint_as_float(sa[4 * g + 3])));
-                            gm[h * 8 + g] = fmaxf(x0, x1);
+                            gm[h * 8 + g] = pair_group_max(sa[4 * g], sa[4 * g + 1], sa[4 * g + 2], sa[4 * g + 3]);
                         } else {
                             const float m = fmaxf(fabsf(__uint_as_float(sa[4 * g])), fabsf(__uint_as_float(sa[4 * g + 1])));
                             gm[h * 8 + g] = max3(m, fabsf(__uint_as_float(sa[4 * g + 2])), fabsf(__uint_as_float(sa[4 * g + 3])));
@@ -497,9 +512,7 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         if (PAIR) {
-                            const float x0 = __fadd_rn(fabsf(__uint_as_float(sb[4 * g])), fabsf(__uint_as_float(sb[4 * g + 1])));
-                            const float x1 = __fadd_rn(fabsf(__uint_as_float(sb[4 * g + 2])), fabsf(__uint_as_float(sb[4 * g + 3])));
-                            gm[h * 8 + 4 + g] = fmaxf(x0, x1);
+                            gm[h * 8 + 4 + g] = pair_group_max(sb[4 * g], sb[4 * g + 1], sb[4 * g + 2], sb[4 * g + 3]);
                         } else {
                             const float m = fmaxf(fabsf(__uint_as_float(sb[4 * g])), fabsf(__uint_as_float(sb[4 * g + 1])));
                             gm[h * 8 + 4 + g] = max3(m, fabsf(__uint_as_float(sb[4 * g + 2])), fabsf(__uint_as_float(sb[4 * g + 3])));
@@ -515,7 +528,10 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
             if (tracer) GQ_TRACE(3, it);
             if (TRACE && quad != 0 && lane == 0) GQ_TRACE(8 + quad, it);   // 9..11: the other quadrants' releases
 
-            // ---- this row's chunk, from the (swizzled) smem tile
+            // ---- this row's chunk, from the (swizzled) smem tile.  The tile landed before its MMA was even
+            //      issued; this thread still has to observe the TMA barrier itself before it reads the data,
+            //      and does so here, off the TMEM turnaround chain (the wait returns at once)
+            mbar_wait_hw(bar_full + 8 * s, ph);
             float v[kD];
             {
                 const uint32_t arow = smem_u32(s_a) + s * kTileBytes + row * kRowBytes;
@@ -544,7 +560,11 @@ hsq_encode_tc2_kernel(const __grid_constant__ CUtensorMap map_grad, const __grid
                 am[q] = fmaxf(am[q], gm[16 * q + 15]);
             }
             const float amax = fmaxf(fmaxf(am[0], am[1]), fmaxf(am[2], am[3]));
-            const float thr = amax - margin * sqrtf(n2);
+            // (sqrt.approx: 1 MUFU instead of the IEEE sequence; its relative error of 2^-22 is inside the
+            //  1e-5 slack of `margin`, and any superset of the candidate set gives the same exact result)
+            float nrm;
+            asm("sqrt.approx.f32 %0, %1;" : "=f"(nrm) : "f"(n2));
+            const float thr = amax - margin * nrm;
             // ---- candidate groups: gm[g] >= thr
             uint32_t clo, chi;
             bool special;
@@ -1033,12 +1053,6 @@ static int launch_variant(const Variant &v, const CUtensorMap &mg, const Enc2 &P
     }
 }
 
-// GQ_TC2_WAIT: bit 0 epilogue warps, bit 1 MMA warp wait with plain try_wait (default 3: both)
-static int wait_mode()
-{
-    if (const char *e = getenv("GQ_TC2_WAIT")) return atoi(e) & 3;
-    return 3;
-}
 
 }  // namespace tc2
 
@@ -1076,7 +1090,6 @@ int hsq_tc2_trace(const float *grad, int64_t n_chunks, const float *codebook, vo
         P.s = (float)(1u << tail->n_bit);
         P.random = tail->random;
     }
-    P.wait_hw = wait_mode();
     const int n_tiles = (int)((n_chunks + kTileM - 1) / kTileM);
     int sms = sm_count();
     if (const char *g = getenv("GQ_TC_GRID")) {
@@ -1164,7 +1177,6 @@ int hsq_encode_tc2(const float *grad, int64_t n_chunks, int d, const float *code
             R.epoch = remote->epoch;
         }
     }
-    P.wait_hw = wait_mode();
     const int n_tiles = (int)((n_chunks + kTileM - 1) / kTileM);
     int sms = sm_count();
     if (const char *g = getenv("GQ_TC_GRID")) {

@@ -422,11 +422,20 @@ int qsgd_encode(const float *grad, int64_t n, const int64_t *chunk_start, int64_
     GQ_CUDA(cudaMemsetAsync(norm, 0, (size_t)n_chunks * 4, st));
     if (fast_ok && chunk_start && ((uintptr_t)grad & 15) == 0) {
         // explicit chunk boundaries (TernGrad): contiguous range per warp, two launches
+        // one CTA-contiguous range per CTA and exactly ONE wave: the grid is the number of CTAs that are
+        // resident at once (8 per SM asked for 1184 CTAs of which 5 / 4 per SM fit: a second, 60 % full wave)
         const int b = qsgd_wire_bits(n_bit);
-        const int grid = grid_for(n, 256 * 4 * 4, 8);
-        GQ_CUDA(launch_pdl(seg_absmax_ranges_kernel<4>, dim3(grid), dim3(256), 0, st, grad, n, chunk_start, (int)n_chunks,
+        auto one_wave = [&](auto kern) {
+            static int per_sm = 0;   // per kernel instantiation (generic lambda)
+            if (per_sm == 0 &&
+                (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0) != cudaSuccess || per_sm < 1))
+                per_sm = 4;
+            return grid_for(n, 256 * 4 * 4, per_sm);
+        };
+        const int grid_a = one_wave(seg_absmax_ranges_kernel<4>);
+        GQ_CUDA(launch_pdl(seg_absmax_ranges_kernel<4>, dim3(grid_a), dim3(256), 0, st, grad, n, chunk_start, (int)n_chunks,
                            reinterpret_cast<uint32_t *>(norm)));
-#define GQ_R(B) GQ_CUDA(launch_pdl(qsgd_quantize_ranges_kernel<B, 4>, dim3(grid), dim3(256), 0, st, grad, n, chunk_start, \
+#define GQ_R(B) GQ_CUDA(launch_pdl(qsgd_quantize_ranges_kernel<B, 4>, dim3(one_wave(qsgd_quantize_ranges_kernel<B, 4>)), dim3(256), 0, st, grad, n, chunk_start, \
                                    (int)n_chunks, s, random, uniforms, seed, offset, (const float *)norm, packed))
         if (b == 4) GQ_R(4);
         else if (b == 8) GQ_R(8);
