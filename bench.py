@@ -52,6 +52,8 @@ def parse_args():
     ap.add_argument("--k-bit", type=int, default=8)
     ap.add_argument("--n-bit", type=int, default=None)
     ap.add_argument("--cr", type=int, default=100)
+    ap.add_argument("--sign-wire", type=str, default="2bit", choices=["2bit", "t5"],
+                    help="SignSGD wire container: 2 bits per element, or base 3 with five elements per byte")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     d = CODEC_DEFAULTS[a.codec]
@@ -77,7 +79,7 @@ def codec_label(a):
     if a.codec == "terngrad":
         return "TernGrad (c-dim 0, 1-bit)"
     if a.codec == "sign":
-        return "SignSGD (ternary)"
+        return "SignSGD (ternary%s)" % (", base-3 wire" if getattr(a, "sign_wire", "2bit") == "t5" else "")
     return "top-k cr=%d" % a.cr
 
 
@@ -99,7 +101,8 @@ def workload_label(a, users):
 def make_args(a, num_users):
     from types import SimpleNamespace
     return SimpleNamespace(c_dim=a.c_dim, k_bit=a.k_bit, n_bit=a.n_bit, no_cuda=False, random=True, cr=a.cr,
-                           ef=False, two_phase=False, mode=a.mode, scale="exp", num_users=num_users)
+                           ef=False, two_phase=False, mode=a.mode, scale="exp", num_users=num_users,
+                           sign_wire=getattr(a, "sign_wire", "2bit"))
 
 
 def algorithmic_bytes(a, n, users):
@@ -116,8 +119,9 @@ def algorithmic_bytes(a, n, users):
         enc = n * (4 + per)
         dec = n * (4 + per * users)
     elif a.codec == "sign":
-        enc = n * 4.25
-        dec = n * (4 + 0.25 * users)
+        w = 0.2 if getattr(a, "sign_wire", "2bit") == "t5" else 0.25
+        enc = n * (4 + w)
+        dec = n * (4 + w * users)
     else:
         enc = n * (4 + 8.0 / a.cr)
         dec = n * (4 + 8.0 * users / a.cr)

@@ -60,6 +60,9 @@ _SIGNATURES = {
                                         c_void_p, c_void_p]),
     "gq_sign_encode": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_void_p]),
     "gq_sign_decode_reduce": (c_int, [c_void_p, c_i64, c_int, c_i64, c_int, c_int, c_void_p, c_void_p]),
+    "gq_sign_t5_bytes": (c_i64, [c_i64]),
+    "gq_sign_encode_t5": (c_int, [c_void_p, c_i64, c_void_p, c_void_p]),
+    "gq_sign_decode_reduce_t5": (c_int, [c_void_p, c_i64, c_int, c_i64, c_int, c_int, c_void_p, c_void_p]),
     "gq_topk_workspace_bytes": (c_size, [c_i64, c_int]),
     "gq_topk_select": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_size, c_void_p]),

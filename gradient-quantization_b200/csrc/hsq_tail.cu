@@ -598,6 +598,7 @@ hsq_decode_reduce_staged_kernel(const uint8_t *__restrict__ codes, const uint8_t
     float4 *s_cb = s_dyn;                                                    // [256][2][4]
     uint8_t *s_stage = reinterpret_cast<uint8_t *>(s_cb + 256 * 8);          // [2][NU][codes 1024 | l 1024]
     float2 *s_lbub = reinterpret_cast<float2 *>(s_stage + 2 * NU * 2 * kStTile);   // [NU][n_seg]
+    int64_t *s_seg = reinterpret_cast<int64_t *>(s_lbub + NU * n_seg);             // [n_seg + 1] tensor boundaries
     __shared__ int64_t s_off[8];
     const int tid = threadIdx.x, lane = tid & 31;
     // warp index through a shuffle: the compiler then knows it is warp-uniform, and the slot loop
@@ -610,6 +611,7 @@ hsq_decode_reduce_staged_kernel(const uint8_t *__restrict__ codes, const uint8_t
     }
     for (int i = tid; i < 256 * 8; i += kDecodeThreads)
         s_cb[i] = __ldg(reinterpret_cast<const float4 *>(codebook) + (i >> 3) * 4 + (i & 3));
+    for (int i = tid; i <= n_seg; i += kDecodeThreads) s_seg[i] = __ldg(seg_start + i);   // (a table of the plan, not of the step)
     __syncthreads();
     pdl_wait();   // the records are complete (and, across GPUs, announced by the barrier kernel)
     if (wait.n > 0) {   // ... or by the peers' encode kernels themselves: wait for every rank's delivery flag
@@ -668,7 +670,7 @@ hsq_decode_reduce_staged_kernel(const uint8_t *__restrict__ codes, const uint8_t
             const int64_t c = c0 + sl * 32 + lane;
             if (c0 + sl * 32 >= n_chunks) break;
             const bool ok = c < n_chunks;
-            const int seg = ok ? cached_segment(segc, seg_start, n_seg, c) : 0;
+            const int seg = ok ? cached_segment_smem(segc, s_seg, n_seg, c) : 0;
             // Three or more users: when the whole slot lies in one tensor (almost always), a lane
             // hands (code, level) of TWO users to the writers in one shuffle and the writers
             // dequantize the norm themselves (same three rounded operations) -- the kernel is bound
@@ -727,7 +729,9 @@ hsq_decode_reduce_staged_kernel(const uint8_t *__restrict__ codes, const uint8_t
                 for (int u = 1; u < NU; ++u) {
                     const float2 p0 = mul2(make_float2(cw[u].x, cw[u].y), nm[u]);
                     const float2 p1 = mul2(make_float2(cw[u].z, cw[u].w), nm[u]);
-                    // scalar adds: see hsq_decode_reduce_warp_kernel
+                    // scalar adds: see hsq_decode_reduce_warp_kernel.  (Packed alternative that stays exact: the
+                    // product as FFMA2 with a -0.0 addend from a kernel argument + FADD2 -- ptxas never fuses an
+                    // fma with an add.  Measured: 46.9 us either way at U = 8; packed ops save no issue slots.)
                     a0.x = __fadd_rn(a0.x, p0.x); a0.y = __fadd_rn(a0.y, p0.y);
                     a1.x = __fadd_rn(a1.x, p1.x); a1.y = __fadd_rn(a1.y, p1.y);
                 }
@@ -761,7 +765,7 @@ static int launch_decode_staged(const void *codes, const void *l, const float *l
                                 int n_seg, float s, int mean, int accumulate, float *out, cudaStream_t st)
 {
     auto kern = hsq_decode_reduce_staged_kernel<NU>;
-    const size_t smem = 256 * 128 + (size_t)2 * NU * 2 * kStTile + (size_t)NU * n_seg * 8;
+    const size_t smem = 256 * 128 + (size_t)2 * NU * 2 * kStTile + (size_t)NU * n_seg * 8 + (size_t)(n_seg + 1) * 8;
     GQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 1;
     GQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kDecodeThreads, smem));

@@ -800,9 +800,184 @@ sign_decode_reduce_kernel(const uint8_t *__restrict__ packed, int64_t user_strid
     }
 }
 
+// ------------------------------------------------- sign, base-3 wire (f4) ---
+// Five ternary digits per byte (3^5 = 243 <= 256): byte = t0 + 3 t1 + 9 t2 + 27 t3 + 81 t4 with the
+// same digit code as the 2-bit form (0 -> 0, 1 -> +1, 2 -> -1): 1.6 bits per element instead of 2.
+// A thread owns 20 consecutive elements = one 32-bit word of the wire (little-endian bytes); the
+// section holds ceil(n / 20) words, elements past n encode as 0.
+__global__ void __launch_bounds__(256)
+sign_encode_t5_kernel(const float *__restrict__ v, int64_t n, uint32_t *__restrict__ packed)
+{
+    pdl_launch_dependents();
+    const int64_t n_words = (n + 19) / 20;
+    pdl_wait();
+    for (int64_t w = (int64_t)blockIdx.x * 256 + threadIdx.x; w < n_words; w += (int64_t)gridDim.x * 256) {
+        const int64_t i0 = w * 20;
+        float x[20];
+        if (i0 + 19 < n) {   // five 16-byte loads of 80 consecutive bytes (the other half of each sector: L1)
+#pragma unroll
+            for (int q = 0; q < 5; ++q) {
+                const float4 t = __ldg(reinterpret_cast<const float4 *>(v + i0) + q);
+                x[4 * q] = t.x; x[4 * q + 1] = t.y; x[4 * q + 2] = t.z; x[4 * q + 3] = t.w;
+            }
+        } else {
+#pragma unroll
+            for (int t = 0; t < 20; ++t) x[t] = (i0 + t < n) ? v[i0 + t] : 0.0f;
+        }
+        uint32_t word = 0u;
+#pragma unroll
+        for (int b = 3; b >= 0; --b) {
+            uint32_t byte = 0u;
+#pragma unroll
+            for (int t = 4; t >= 0; --t) {
+                const float e = x[5 * b + t];
+                byte = byte * 3u + (e > 0.0f ? 1u : (e < 0.0f ? 2u : 0u));
+            }
+            word = (word << 8) | byte;
+        }
+        packed[w] = word;
+    }
+}
+
+// A warp decodes 640 elements at a time: lane L takes word L of every user (one coalesced 128-byte
+// request per user), sums its 20 values in user order, and the warp transposes the 640 results through
+// shared memory so that the stores are five fully coalesced 512-byte rows (see sign_decode_reduce_kernel).
+template <int U_>
+__global__ void __launch_bounds__(256)
+sign_decode_reduce_t5_kernel(const uint32_t *__restrict__ packed, int64_t user_stride_words, int n_users_rt,
+                             int64_t n, float inv_u, float div_u, int accumulate, float *__restrict__ out)
+{
+    __shared__ float4 s_t[8][160];   // per warp: 640 floats
+    pdl_launch_dependents();
+    const int n_users = U_ > 0 ? U_ : n_users_rt;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t n_tiles = (n + 639) / 640;
+    const int64_t n_words = (n + 19) / 20;
+    const bool aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    pdl_wait();
+    for (int64_t tile = (int64_t)blockIdx.x * 8 + warp; tile < n_tiles; tile += (int64_t)gridDim.x * 8) {
+        const int64_t e0 = tile * 640;
+        const int64_t w = tile * 32 + lane;
+        float acc[20];
+        for (int u = 0; u < n_users; ++u) {
+            uint32_t word = (w < n_words) ? __ldg(packed + u * user_stride_words + w) : 0u;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                uint32_t by = word & 0xffu;
+                word >>= 8;
+#pragma unroll
+                for (int t = 0; t < 5; ++t) {
+                    const uint32_t q = (by * 171u) >> 9;   // by / 3 for by < 256
+                    const uint32_t c = by - 3u * q;
+                    by = q;
+                    const float val = (c == 1u) ? 1.0f : ((c == 2u) ? -1.0f : 0.0f);
+                    acc[5 * b + t] = (u == 0) ? val : __fadd_rn(acc[5 * b + t], val);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 20; ++k) {
+            if (inv_u != 0.0f) acc[k] = __fmul_rn(acc[k], inv_u);
+            else if (div_u != 0.0f) acc[k] = __fdiv_rn(acc[k], div_u);
+        }
+        // lane L holds elements 20 L .. 20 L + 19 = float4 groups 5 L .. 5 L + 4 of the tile
+#pragma unroll
+        for (int q = 0; q < 5; ++q) s_t[warp][5 * lane + q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            float4 r = s_t[warp][32 * q + lane];
+            const int64_t i = e0 + 4 * (32 * q + lane);
+            if (aligned && i + 3 < n) {
+                float4 *op = reinterpret_cast<float4 *>(out + i);
+                if (accumulate) {
+                    const float4 o = *op;
+                    r.x = (accumulate == 2) ? __fsub_rn(o.x, r.x) : __fadd_rn(o.x, r.x);
+                    r.y = (accumulate == 2) ? __fsub_rn(o.y, r.y) : __fadd_rn(o.y, r.y);
+                    r.z = (accumulate == 2) ? __fsub_rn(o.z, r.z) : __fadd_rn(o.z, r.z);
+                    r.w = (accumulate == 2) ? __fsub_rn(o.w, r.w) : __fadd_rn(o.w, r.w);
+                }
+                *op = r;
+            } else {
+                const float y[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (i + k >= n) continue;
+                    float x = y[k];
+                    if (accumulate) x = (accumulate == 2) ? __fsub_rn(out[i + k], x) : __fadd_rn(out[i + k], x);
+                    out[i + k] = x;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+int sign_encode_t5(const float *grad, int64_t n, uint32_t *packed, cudaStream_t st)
+{
+    if (n == 0) return GQ_OK;
+    GQ_CUDA(launch_pdl(sign_encode_t5_kernel, dim3(grid_for((n + 19) / 20, 256, 16)), dim3(256), 0, st, grad, n, packed));
+    GQ_LAUNCH_CHECK("sign_encode_t5");
+    return GQ_OK;
+}
+
+int sign_decode_reduce_t5(const uint32_t *packed, int64_t user_stride_words, int n_users, int64_t n, int mean,
+                          int accumulate, float *out, cudaStream_t st)
+{
+    if (n == 0) return GQ_OK;
+    float inv_u, div_u;
+    mean_factors(mean, n_users, &inv_u, &div_u);
+    const int grid = grid_for((n + 639) / 640, 8, 8);
+#define GQ_S(UU) GQ_CUDA(launch_pdl(sign_decode_reduce_t5_kernel<UU>, dim3(grid), dim3(256), 0, st, packed, user_stride_words, \
+                                    n_users, n, inv_u, div_u, accumulate, out))
+    if (n_users == 1) GQ_S(1);
+    else if (n_users == 2) GQ_S(2);
+    else if (n_users == 4) GQ_S(4);
+    else if (n_users == 8) GQ_S(8);
+    else GQ_S(0);
+#undef GQ_S
+    GQ_LAUNCH_CHECK("sign_decode_reduce_t5");
+    return GQ_OK;
+}
+
+// packed output only (the fused plan): a thread owns 16 consecutive elements = one 32-bit word of the
+// wire -- four 16-byte loads in flight per thread and a coalesced 128-byte store per warp instead of 32
+// single bytes (21.0 -> see DESIGN.md section 8)
+__global__ void __launch_bounds__(256)
+sign_encode_words_kernel(const float *__restrict__ v, int64_t n, uint32_t *__restrict__ packed)
+{
+    pdl_launch_dependents();
+    const int64_t n_words = n / 16;   // whole words; the ragged tail goes through sign_encode_kernel
+    pdl_wait();
+    for (int64_t w = (int64_t)blockIdx.x * 256 + threadIdx.x; w < n_words; w += (int64_t)gridDim.x * 256) {
+        float4 t[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) t[q] = __ldg(reinterpret_cast<const float4 *>(v) + 4 * w + q);
+        uint32_t word = 0u;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float x[4] = {t[q].x, t[q].y, t[q].z, t[q].w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                word |= ((x[k] > 0.0f ? 1u : 0u) | (x[k] < 0.0f ? 2u : 0u)) << (8 * q + 2 * k);
+        }
+        packed[w] = word;
+    }
+}
+
 int sign_encode(const float *grad, int64_t n, float *out_f32, uint8_t *packed, cudaStream_t st)
 {
     if (n == 0) return GQ_OK;
+    if (!out_f32 && packed && ((uintptr_t)packed & 3) == 0 && n >= 16) {
+        const int64_t n_words = n / 16;
+        GQ_CUDA(launch_pdl(sign_encode_words_kernel, dim3(grid_for(n_words, 256, 16)), dim3(256), 0, st, grad, n,
+                           reinterpret_cast<uint32_t *>(packed)));
+        const int64_t done = n_words * 16;
+        if (done < n)   // at most 15 elements
+            sign_encode_kernel<<<1, 32, 0, st>>>(grad + done, n - done, nullptr, packed + done / 4);
+        GQ_LAUNCH_CHECK("sign_encode");
+        return GQ_OK;
+    }
     sign_encode_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, st>>>(grad, n, out_f32, packed);
     GQ_LAUNCH_CHECK("sign_encode");
     return GQ_OK;
@@ -888,6 +1063,24 @@ int gq_sign_decode_reduce(const uint8_t *packed, int64_t user_stride_bytes, int 
     GQ_REQUIRE(n >= 0 && n_users >= 1 && (n == 0 || (packed && out)), "bad arguments");
     return sign_decode_reduce(packed, user_stride_bytes, n_users, n, mean, accumulate, out,
                               as_stream(stream));
+}
+
+int64_t gq_sign_t5_bytes(int64_t n) { return n <= 0 ? 0 : (n + 19) / 20 * 4; }
+
+int gq_sign_encode_t5(const float *grad, int64_t n, void *packed, gq_stream_t stream)
+{
+    GQ_REQUIRE(n >= 0 && (n == 0 || (grad && packed)), "bad arguments");
+    GQ_REQUIRE(((uintptr_t)grad & 15) == 0 && ((uintptr_t)packed & 3) == 0, "gradient 16-byte, wire 4-byte aligned");
+    return sign_encode_t5(grad, n, reinterpret_cast<uint32_t *>(packed), as_stream(stream));
+}
+
+int gq_sign_decode_reduce_t5(const void *packed, int64_t user_stride_bytes, int n_users, int64_t n, int mean,
+                             int accumulate, float *out, gq_stream_t stream)
+{
+    GQ_REQUIRE(n >= 0 && n_users >= 1 && (n == 0 || (packed && out)), "bad arguments");
+    GQ_REQUIRE(((uintptr_t)packed & 3) == 0 && (user_stride_bytes & 3) == 0, "wire sections are 4-byte aligned");
+    return sign_decode_reduce_t5(reinterpret_cast<const uint32_t *>(packed), user_stride_bytes / 4, n_users, n, mean,
+                                 accumulate, out, as_stream(stream));
 }
 
 }  // extern "C"

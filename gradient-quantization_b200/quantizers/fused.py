@@ -8,7 +8,7 @@ user's compressed form is one contiguous *packed record*:
 
     record = [ per HSQ group : codes | l (or fp32 norms) | lb/ub table ]
              [ per QSGD group: chunk norms | packed sign+level          ]
-             [ sign group    : 2-bit packed signs                       ]
+             [ sign group    : 2-bit packed signs (or base-3, 5 per byte)   ]
              [ top-k group   : int32 indices | fp32 values              ]
              [ identity      : raw fp32 (tensors with <= 1000 elements) ]
 
@@ -180,8 +180,12 @@ class FusedPlan:
                 g.packed_off = rec
                 rec += _up((g.n + 3) // 4 * 4 * g.bits // 8)
             elif g.kind == "sign":
+                # wire container: 2 bits per element (default) or the base-3 form, five elements per byte
+                # (args.sign_wire = "t5"); the decoded values are the same
+                g.t5 = getattr(a, "sign_wire", "2bit") == "t5"
+                g.wire_bytes = int(_lib.value("gq_sign_t5_bytes", g.n)) if g.t5 else (g.n + 3) // 4
                 g.packed_off = rec
-                rec += _up((g.n + 3) // 4)
+                rec += _up(g.wire_bytes)
             elif g.kind == "topk":
                 g.n_seg = len(g.tensors)
                 starts, ks, kp = [0], [], [0]
@@ -263,7 +267,7 @@ class FusedPlan:
                 elif g.kind == "qsgd":
                     out.append((g.norm_off, g.packed_off + _up((g.n + 3) // 4 * 4 * g.bits // 8)))
                 elif g.kind == "sign":
-                    out.append((g.packed_off, g.packed_off + _up((g.n + 3) // 4)))
+                    out.append((g.packed_off, g.packed_off + _up(g.wire_bytes)))
                 elif g.kind == "topk":
                     out.append((g.idx_off, g.val_off + _up(g.k_total * 4)))
                 elif g.kind == "identity" and g.n:
@@ -330,7 +334,7 @@ class FusedPlan:
             elif g.kind == "qsgd":
                 b += g.n_chunks * 4 + (g.n * g.bits + 7) // 8
             elif g.kind == "sign":
-                b += (g.n + 3) // 4
+                b += g.wire_bytes
             elif g.kind == "topk":
                 b += g.k_total * 8
             else:
@@ -431,7 +435,10 @@ class FusedPlan:
                           self.random, _lib.ptr(r), seed, off, base + g.norm_off, None, None,
                           base + g.packed_off, st)
             elif g.kind == "sign":
-                _lib.call("gq_sign_encode", gp, g.n, None, base + g.packed_off, st)
+                if g.t5:
+                    _lib.call("gq_sign_encode_t5", gp, g.n, base + g.packed_off, st)
+                else:
+                    _lib.call("gq_sign_encode", gp, g.n, None, base + g.packed_off, st)
             elif g.kind == "topk":
                 _lib.call("gq_topk_select", gp, g.n, _lib.ptr(g.seg_start), _lib.ptr(g.k),
                           _lib.ptr(g.k_prefix), g.n_seg, None, base + g.idx_off, base + g.val_off,
@@ -541,8 +548,8 @@ class FusedPlan:
                 _lib.call("gq_qsgd_decode_reduce", base + g.norm_off, base + g.packed_off, stride, n_users,
                           g.n, _lib.ptr(g.chunk_start), g.n_chunks, g.dim, g.n_bit, mean, acc, op, st)
             elif g.kind == "sign":
-                _lib.call("gq_sign_decode_reduce", base + g.packed_off, stride, n_users, g.n, mean, acc,
-                          op, st)
+                _lib.call("gq_sign_decode_reduce_t5" if g.t5 else "gq_sign_decode_reduce", base + g.packed_off, stride,
+                          n_users, g.n, mean, acc, op, st)
             elif g.kind == "topk":
                 _lib.call("gq_topk_scatter_reduce", base + g.idx_off, base + g.val_off, stride, n_users,
                           g.k_total, g.n, mean, acc, op, st)

@@ -200,6 +200,16 @@ int gq_sign_encode(const float *grad, int64_t n, float *out_f32, uint8_t *packed
 int gq_sign_decode_reduce(const uint8_t *packed, int64_t user_stride_bytes, int n_users, int64_t n,
                           int mean, int accumulate, float *out, gq_stream_t stream);
 
+/* The same codec on the denser base-3 wire (SURVEY 8f-4 "ternary sign 5-per-byte"): five elements per
+ * byte, byte = t0 + 3 t1 + 9 t2 + 27 t3 + 81 t4 with the digit code of the 2-bit form (0 -> 0, 1 -> +1,
+ * 2 -> -1); 20 elements per little-endian 32-bit word, gq_sign_t5_bytes(n) = 4 * ceil(n / 20) bytes per
+ * section (elements past n encode as 0).  Decoded values are those of gq_sign_decode_reduce, bit for bit
+ * (compressors/signsgd_compressor.py:8-12 fixes only the values, not the container). */
+int64_t gq_sign_t5_bytes(int64_t n);
+int gq_sign_encode_t5(const float *grad, int64_t n, void *packed, gq_stream_t stream);
+int gq_sign_decode_reduce_t5(const void *packed, int64_t user_stride_bytes, int n_users, int64_t n,
+                             int mean, int accumulate, float *out, gq_stream_t stream);
+
 /* ------------------------------------------------------------------------- */
 /* Top-k sparsification.  Replaces TopKSparsificationCompressor.compress
  *   (compressors/topk_sparsification_compressor.py:18-23): per tensor

@@ -285,6 +285,24 @@ class Sign:
         return sig.reshape(self.shape)
 
 
+def sign_pack_t5(sig):
+    """Base-3 wire of a ternary sign vector (include/gqb200.h gq_sign_encode_t5): five elements per byte,
+    byte = t0 + 3 t1 + 9 t2 + 27 t3 + 81 t4, digit 0 -> 0, 1 -> +1, 2 -> -1; padded with zeros to a
+    multiple of 20 elements (whole 32-bit words)."""
+    v = np.asarray(sig, np.float32).reshape(-1)
+    n = v.size
+    t = np.zeros((n + 19) // 20 * 20, np.uint8)
+    t[:n] = np.where(v > 0, 1, np.where(v < 0, 2, 0))
+    w = np.array([1, 3, 9, 27, 81], np.uint16)
+    return (t.reshape(-1, 5).astype(np.uint16) * w).sum(1).astype(np.uint8)
+
+
+def sign_unpack_t5(packed, n):
+    b = np.asarray(packed, np.uint8).astype(np.int32)
+    digits = np.stack([(b // d) % 3 for d in (1, 3, 9, 27, 81)], axis=1).reshape(-1)[:n]
+    return np.where(digits == 1, 1.0, np.where(digits == 2, -1.0, 0.0)).astype(np.float32)
+
+
 class TopK:
     def __init__(self, size, shape, cr):
         self.shape, self.k = tuple(shape), size // cr

@@ -194,6 +194,55 @@ def test_sign_packed_mean():
         assert np.array_equal(plan.view(i, out).cpu().numpy().reshape(-1), ref), i
 
 
+@pytest.mark.parametrize("U", [1, 2, 3, 8])
+def test_sign_base3_wire(U):
+    """args.sign_wire = "t5" (five ternary digits per byte): the wire bytes equal the oracle's
+    packing of the reference's sign() output, the record shrinks to 1.6 bits per element, and the fused
+    decode gives the 2-bit wire's values bit for bit -- ragged sizes (not multiples of 20), exact zeros."""
+    from gq_b200.quantizers.fused import FusedPlan
+    shapes = [(64, 128), (100,), (1031,), (7, 643), (20 * 640 + 13,)]
+    a5, a2 = make_args(num_users=U, sign_wire="t5"), make_args(num_users=U)
+    plan = FusedPlan(gq_b200.SignSGDCompressor, shapes, a5, torch.device(DEV), U)
+    plan2 = FusedPlan(gq_b200.SignSGDCompressor, shapes, a2, torch.device(DEV), U)
+    sizes = [int(np.prod(s)) for s in shapes]
+    g = plan.groups[0]
+    assert g.kind == "sign" and g.t5 and g.wire_bytes == (g.n + 19) // 20 * 4
+    assert plan.wire_bytes() < plan2.wire_bytes() and g.wire_bytes * 5 <= (g.n + 19) // 20 * 20
+    decs = []
+    for u in range(U):
+        xs = [gen_input(650 + 10 * u + i, n).reshape(s) for i, (n, s) in enumerate(zip(sizes, shapes))]
+        xs[0][0, :7] = 0.0
+        xs[3][2, 100:140] = -0.0
+        for p_ in (plan, plan2):
+            p_.gather([_t(x) for x in xs])
+            p_.encode(u)
+        # the wire itself: group order = tensors with more than 1000 elements, in plan order
+        flat = np.concatenate([O.sign(xs[i]).reshape(-1) for i in g.tensors])
+        wire = plan.records[u][g.packed_off:g.packed_off + g.wire_bytes].cpu().numpy()
+        assert np.array_equal(wire, O.sign_pack_t5(flat)), u
+        assert np.array_equal(O.sign_unpack_t5(wire, g.n), flat)
+        decs.append([O.sign(x).reshape(x.shape) if x.size > 1000 else x for x in xs])
+    for mean in (True, False):
+        out, out2 = plan.decode(mean=mean), plan2.decode(mean=mean)
+        assert torch.equal(out, out2)
+        for i in range(len(shapes)):
+            st = np.stack([decs[u][i].reshape(-1) for u in range(U)])
+            if mean:
+                ref = O.ps_mean(st)
+            else:           # plain sum in user order, fp32
+                ref = st[0].copy()
+                for u in range(1, U):
+                    ref = (ref + st[u]).astype(np.float32)
+            assert np.array_equal(plan.view(i, out).cpu().numpy().reshape(-1), ref), (mean, i)
+    # decode-accumulate (ring hop) and decode-subtract (error feedback) agree with the 2-bit wire too
+    base = torch.randn_like(plan.arena)
+    for acc in (1, 2):
+        o5, o2 = base.clone(), base.clone()
+        plan.decode(first_user=0, n_users=1, mean=False, accumulate=acc, out=o5)
+        plan2.decode(first_user=0, n_users=1, mean=False, accumulate=acc, out=o2)
+        assert torch.equal(o5, o2), acc
+
+
 @pytest.mark.parametrize("d,k_bit", [(16, 8), (8, 8), (32, 8)])
 def test_pvc_and_residual_vs_oracle(d, k_bit):
     """PVC implements the reference's intended algorithm (parity unpinned); the CUDA kernel

@@ -155,3 +155,16 @@ def test_hsq_codeword_input_recovers_itself():
     codes, u = O.hsq_search(x, cb)
     assert list(codes) == [3, 200, 17]
     assert np.allclose(u, [0.5, -2.0, 1e-3], rtol=1e-6)
+
+
+def test_sign_base3_wire_packing_roundtrip():
+    """oracle.sign_pack_t5 / sign_unpack_t5 (the checker of gq_sign_encode_t5): five ternary digits per byte,
+    sections padded to whole 32-bit words, every ternary vector survives the round trip."""
+    rs = np.random.RandomState(3)
+    for n in (1, 4, 5, 19, 20, 21, 640, 1031, 12813):
+        sig = rs.randint(-1, 2, n).astype(np.float32)
+        w = O.sign_pack_t5(sig)
+        assert w.dtype == np.uint8 and w.size == (n + 19) // 20 * 4 and int(w.max()) <= 242
+        assert np.array_equal(O.sign_unpack_t5(w, n), sig)
+    # the digit code and the digit order
+    assert O.sign_pack_t5(np.array([1, -1, 0, 0, 1], np.float32))[0] == 1 + 3 * 2 + 81 * 1
