@@ -243,6 +243,7 @@ qsgd_encode_chunks_kernel(const float *__restrict__ v, int64_t n_chunks, int dim
 // TernGrad (one chunk per tensor): every warp walks increasing addresses of one CTA-owned range, so
 // the chunk of its elements changes a handful of times: running maximum in registers and one
 // atomicMax per (warp, chunk) in the first kernel, one norm load per chunk change in the second.
+constexpr int kRangeTable = 1023;   // tensors per group whose boundaries fit the shared-memory table
 template <int UN>
 __global__ void __launch_bounds__(256)
 seg_absmax_ranges_kernel(const float *__restrict__ v, int64_t n, const int64_t *__restrict__ chunk_start,
@@ -255,6 +256,16 @@ seg_absmax_ranges_kernel(const float *__restrict__ v, int64_t n, const int64_t *
     const int64_t span = 128 * UN;
     const int64_t R = ((n + gridDim.x - 1) / gridDim.x + 8 * span - 1) / (8 * span) * (8 * span);
     const int64_t e_begin = (int64_t)blockIdx.x * R + (threadIdx.x >> 5) * span, e_end = min(n, (int64_t)(blockIdx.x + 1) * R);
+    // (a moving front -- the whole grid on adjacent spans, a flush per iteration -- measured 53-60 us against
+    //  35-39 us for the ranges; eight loads per thread instead of four: 67 us)
+    // tensor boundaries in shared memory: the lookup at a boundary is a binary search of shared-memory
+    // loads instead of dependent L2 round trips (the table belongs to the plan: readable before the wait)
+    __shared__ int64_t s_start[kRangeTable + 1];
+    const bool tab = n_chunks <= kRangeTable;
+    if (tab) {
+        for (int i = threadIdx.x; i <= n_chunks; i += 256) s_start[i] = __ldg(chunk_start + i);
+        __syncthreads();
+    }
     SegCache sc;
     int cur = -1;
     uint32_t cur_max = 0u;
@@ -283,7 +294,7 @@ seg_absmax_ranges_kernel(const float *__restrict__ v, int64_t n, const int64_t *
                 x[t] = make_float4(y[0], y[1], y[2], y[3]);
             }
         }
-        const int first = cached_segment(sc, chunk_start, n_chunks, e0);
+        const int first = tab ? cached_segment_smem(sc, s_start, n_chunks, e0) : cached_segment(sc, chunk_start, n_chunks, e0);
         if (e1 <= sc.hi) {   // the whole span lies in one chunk (warp-uniform)
             if (first != cur) { flush(); cur = first; }
 #pragma unroll
@@ -302,7 +313,8 @@ seg_absmax_ranges_kernel(const float *__restrict__ v, int64_t n, const int64_t *
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     if (i0 + k < e1)
-                        atomicMax(norm_bits + find_segment(chunk_start, n_chunks, i0 + k),
+                        atomicMax(norm_bits + (tab ? find_segment_smem(s_start, n_chunks, i0 + k)
+                                                   : find_segment(chunk_start, n_chunks, i0 + k)),
                                   __float_as_uint(y[k]) & 0x7fffffffu);
             }
         }
@@ -324,6 +336,12 @@ qsgd_quantize_ranges_kernel(const float *__restrict__ v, int64_t n, const int64_
     const int64_t span = 128 * UN;
     const int64_t R = ((n + gridDim.x - 1) / gridDim.x + 8 * span - 1) / (8 * span) * (8 * span);
     const int64_t e_begin = (int64_t)blockIdx.x * R + (threadIdx.x >> 5) * span, e_end = min(n, (int64_t)(blockIdx.x + 1) * R);
+    __shared__ int64_t s_start[kRangeTable + 1];
+    const bool tab = n_chunks <= kRangeTable;
+    if (tab) {
+        for (int i = threadIdx.x; i <= n_chunks; i += 256) s_start[i] = __ldg(chunk_start + i);
+        __syncthreads();
+    }
     SegCache sc;
     int cur = -1;
     float nm_cur = 0.0f;
@@ -344,7 +362,7 @@ qsgd_quantize_ranges_kernel(const float *__restrict__ v, int64_t n, const int64_
                 x[t] = make_float4(y[0], y[1], y[2], y[3]);
             }
         }
-        const int first = cached_segment(sc, chunk_start, n_chunks, e0);
+        const int first = tab ? cached_segment_smem(sc, s_start, n_chunks, e0) : cached_segment(sc, chunk_start, n_chunks, e0);
         const bool uniform = e1 <= sc.hi;
         if (uniform && first != cur) {
             cur = first;
@@ -373,7 +391,9 @@ qsgd_quantize_ranges_kernel(const float *__restrict__ v, int64_t n, const int64_
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     if (i0 + k >= e1) { pk[k] = 0u; continue; }
-                    const float nm = uniform ? nm_cur : __ldcg(norm + find_segment(chunk_start, n_chunks, i0 + k));
+                    const float nm = uniform ? nm_cur
+                                             : __ldcg(norm + (tab ? find_segment_smem(s_start, n_chunks, i0 + k)
+                                                                  : find_segment(chunk_start, n_chunks, i0 + k)));
                     pk[k] = ((y[k] > 0.0f ? 1u : 0u) << (BITS - 1)) | qsgd_level_packed(y[k], nm, s, random, r[k]);
                 }
             }
