@@ -76,6 +76,12 @@ print("  total for the CTA: %d cycles for %d tiles" % (ev[7, tiles - 1], tiles))
 rel_all = np.stack([t[3, :tiles], t[9, :tiles], t[10, :tiles], t[11, :tiles]]) - t0
 last_rel = rel_all.max(axis=0)
 print("  quad release skew (last quad - quad 0)        : %.0f   (last quad - first quad: %.0f)" % (np.mean(last_rel[sl] - ev[3, sl]), np.mean(last_rel[sl] - rel_all.min(axis=0)[sl])))
+first_rel = rel_all.min(axis=0)
+print("  per-quadrant release - first release (mean)   : " + "  ".join("q%d %.0f" % (q, np.mean(rel_all[q, sl] - first_rel[sl])) for q in range(4)))
+print("  which quadrant is last (share of tiles)       : " + "  ".join("q%d %.0f%%" % (q, 100.0 * np.mean(rel_all[:, sl].argmax(axis=0) == q)) for q in range(4)))
+for grp in range(3):
+    idx = np.arange(lo + ((grp - lo) % 3), hi, 3)
+    print("  group %d: quadrant release - first (mean)       : " % grp + "  ".join("q%d %.0f" % (q, np.mean(rel_all[q, idx] - first_rel[idx])) for q in range(4)))
 m_fu = t[12, :tiles] - t0
 m_te = t[13, :tiles] - t0
 obs = t[14, :tiles] - t0
