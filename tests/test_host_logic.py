@@ -188,3 +188,18 @@ def test_ring_stages_cut_the_resnet50_plan_at_aligned_tensor_boundaries():
             seen[b:e] += 1
     for off, n in ((g.codes_off, g.n_chunks), (g.l_off, g.n_chunks), (g.lbub_off, 8 * g.n_seg)):
         assert (seen[off:off + n] == 1).all()
+
+
+def test_sign_wire_containers_in_the_plan_layout():
+    """SignSGD record: 2 bits per element by default, base 3 (five elements per byte, whole 32-bit words) with
+    args.sign_wire = "t5" (INTEGRATION.md section 3); everything else of the layout is unchanged."""
+    shapes = resnet50_shapes()
+    p2 = FusedPlan(gq_b200.SignSGDCompressor, shapes, make_args(), torch.device("cpu"), 1)
+    p5 = FusedPlan(gq_b200.SignSGDCompressor, shapes, make_args(sign_wire="t5"), torch.device("cpu"), 1)
+    g2, g5 = p2.groups[0], p5.groups[0]
+    assert g2.kind == g5.kind == "sign" and g2.n == g5.n == 23498432
+    assert not g2.t5 and g2.wire_bytes == g2.n // 4
+    assert g5.t5 and g5.wire_bytes == (g5.n + 19) // 20 * 4
+    assert p5.wire_bytes() == p2.wire_bytes() - g2.wire_bytes + g5.wire_bytes
+    assert 0.79 < g5.wire_bytes / g2.wire_bytes < 0.81            # 1.6 instead of 2 bits per element
+    assert p5.record_bytes % 256 == 0 and p5.tensor_off == p2.tensor_off
