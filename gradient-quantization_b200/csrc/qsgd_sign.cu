@@ -183,7 +183,7 @@ template <int BITS, int NV, int LPC, int UNR>
 __global__ void __launch_bounds__(256)
 qsgd_encode_chunks_kernel(const float *__restrict__ v, int64_t n_chunks, int dim, float s, int random,
                           const float *__restrict__ uniforms, uint64_t seed, uint64_t offset,
-                          float *__restrict__ norm, void *__restrict__ packed)
+                          float *__restrict__ norm, void *__restrict__ packed, const Rider rider)
 {
     pdl_launch_dependents();
     const int dim4 = dim >> 2;
@@ -192,6 +192,7 @@ qsgd_encode_chunks_kernel(const float *__restrict__ v, int64_t n_chunks, int dim
     const int64_t slot = ((int64_t)blockIdx.x * 256 + threadIdx.x) / LPC;
     const int64_t warp_slot0 = (((int64_t)blockIdx.x * 256 + threadIdx.x) & ~31ll) / LPC;
     pdl_wait();
+    rider_run(rider, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);   // identity tensors ride along
     for (int64_t base = 0; base + warp_slot0 < n_chunks; base += n_slots * UNR) {   // warp-uniform trip count
         float4 x[UNR][NV];
         int64_t c[UNR];
@@ -247,7 +248,7 @@ constexpr int kRangeTable = 1023;   // tensors per group whose boundaries fit th
 template <int UN>
 __global__ void __launch_bounds__(256)
 seg_absmax_ranges_kernel(const float *__restrict__ v, int64_t n, const int64_t *__restrict__ chunk_start,
-                         int n_chunks, uint32_t *__restrict__ norm_bits)
+                         int n_chunks, uint32_t *__restrict__ norm_bits, const Rider rider)
 {
     pdl_launch_dependents();
     // every CTA owns a contiguous range, its eight warps take the spans of that range in turn (the
@@ -270,6 +271,7 @@ seg_absmax_ranges_kernel(const float *__restrict__ v, int64_t n, const int64_t *
     int cur = -1;
     uint32_t cur_max = 0u;
     pdl_wait();
+    rider_run(rider, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);   // identity tensors ride along
     auto flush = [&]() {
         if (cur >= 0) {
             const uint32_t w = __reduce_max_sync(0xffffffffu, cur_max);
@@ -413,6 +415,7 @@ int qsgd_encode(const float *grad, int64_t n, const int64_t *chunk_start, int64_
     const bool fast_ok = packed && !signs && !l && ((uintptr_t)packed & 15) == 0 && n_chunks < (1ll << 31);
     if (fast_ok && !chunk_start && dim % 4 == 0 && dim <= 2048) {
         // one launch: chunk norms and packed levels from registers
+        const Rider rider = take_rider();   // a pending identity copy rides in this launch
         const int b = qsgd_wire_bits(n_bit);
         const int dim4 = dim / 4;
         const int lpc = dim4 <= 8 ? 8 : 32;
@@ -421,7 +424,7 @@ int qsgd_encode(const float *grad, int64_t n, const int64_t *chunk_start, int64_
         const int64_t per_block = (int64_t)(256 / lpc) * unr;
         const int grid = grid_for(n_chunks, (int)per_block, 16);
 #define GQ_E(B, NV, LPC, UNR) GQ_CUDA(launch_pdl(qsgd_encode_chunks_kernel<B, NV, LPC, UNR>, dim3(grid), dim3(256), 0, st, \
-                                       grad, n_chunks, dim, s, random, uniforms, seed, offset, norm, packed))
+                                       grad, n_chunks, dim, s, random, uniforms, seed, offset, norm, packed, rider))
 #define GQ_EB(B)                                                  \
         do {                                                      \
             if (lpc == 8) GQ_E(B, 1, 8, 4);                       \
@@ -453,8 +456,9 @@ int qsgd_encode(const float *grad, int64_t n, const int64_t *chunk_start, int64_
             return grid_for(n, 256 * 4 * 4, per_sm);
         };
         const int grid_a = one_wave(seg_absmax_ranges_kernel<4>);
+        const Rider rider = take_rider();   // a pending identity copy rides in the first pass
         GQ_CUDA(launch_pdl(seg_absmax_ranges_kernel<4>, dim3(grid_a), dim3(256), 0, st, grad, n, chunk_start, (int)n_chunks,
-                           reinterpret_cast<uint32_t *>(norm)));
+                           reinterpret_cast<uint32_t *>(norm), rider));
 #define GQ_R(B) GQ_CUDA(launch_pdl(qsgd_quantize_ranges_kernel<B, 4>, dim3(one_wave(qsgd_quantize_ranges_kernel<B, 4>)), dim3(256), 0, st, grad, n, chunk_start, \
                                    (int)n_chunks, s, random, uniforms, seed, offset, (const float *)norm, packed))
         if (b == 4) GQ_R(4);
@@ -542,13 +546,14 @@ __global__ void __launch_bounds__(256)
 qsgd_decode_reduce8_kernel(const float *__restrict__ norm, const void *__restrict__ packed, int64_t user_stride,
                            int n_users_rt, int64_t n, const int64_t *__restrict__ chunk_start, int n_chunks,
                            uint32_t dim, float inv_s, float inv_u, float div_u, int accumulate,
-                           float *__restrict__ out)
+                           float *__restrict__ out, const Rider rider)
 {
     pdl_launch_dependents();
     const int n_users = U_ > 0 ? U_ : n_users_rt;
     const int64_t n8 = n >> 3;
     SegCache sc;
     pdl_wait();
+    rider_run(rider, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);   // identity tensors ride along
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 255) {
         // the last n % 8 elements, one by one
         for (int64_t i = n8 * 8; i < n; ++i) {
@@ -664,8 +669,9 @@ int qsgd_decode_reduce(const float *norm, const void *packed, int64_t user_strid
         float inv_u, div_u;
         mean_factors(mean, n_users, &inv_u, &div_u);
         const int grid8 = grid_for(n8 + 1, 256, 16);
+        const Rider rider = take_rider();   // a pending identity reduction rides in this launch
 #define GQ_D8(B, UU) GQ_CUDA(launch_pdl(qsgd_decode_reduce8_kernel<B, UU>, dim3(grid8), dim3(256), 0, st, norm, packed, user_stride, \
-                                        n_users, n, chunk_start, (int)n_chunks, (uint32_t)(dim > 0 ? dim : 1), 1.0f / s, inv_u, div_u, accumulate, out))
+                                        n_users, n, chunk_start, (int)n_chunks, (uint32_t)(dim > 0 ? dim : 1), 1.0f / s, inv_u, div_u, accumulate, out, rider))
 #define GQ_D8B(B) do { if (n_users == 1) GQ_D8(B, 1); else if (n_users == 2) GQ_D8(B, 2); else if (n_users == 4) GQ_D8(B, 4); \
                        else if (n_users == 8) GQ_D8(B, 8); else GQ_D8(B, 0); } while (0)
         if (bits == 4) GQ_D8B(4);
@@ -753,7 +759,7 @@ sign_encode_kernel(const float *__restrict__ v, int64_t n, float *__restrict__ o
 template <int U_>
 __global__ void __launch_bounds__(256)
 sign_decode_reduce_kernel(const uint8_t *__restrict__ packed, int64_t user_stride, int n_users_rt,
-                          int64_t n, float inv_u, float div_u, int accumulate, float *__restrict__ out)
+                          int64_t n, float inv_u, float div_u, int accumulate, float *__restrict__ out, const Rider rider)
 {
     pdl_launch_dependents();
     const int n_users = U_ > 0 ? U_ : n_users_rt;
@@ -762,6 +768,7 @@ sign_decode_reduce_kernel(const uint8_t *__restrict__ packed, int64_t user_strid
     const bool aligned = ((reinterpret_cast<uintptr_t>(out) & 15) == 0) && ((user_stride & 3) == 0) &&
                          ((reinterpret_cast<uintptr_t>(packed) & 3) == 0);
     pdl_wait();
+    rider_run(rider, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);   // identity tensors ride along
     for (int64_t tile = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); tile < n_tiles; tile += (int64_t)gridDim.x * 8) {
         const int64_t e0 = tile * 512;
         const bool full = aligned && (e0 + 511 < n);   // warp-uniform
@@ -826,11 +833,12 @@ sign_decode_reduce_kernel(const uint8_t *__restrict__ packed, int64_t user_strid
 // A thread owns 20 consecutive elements = one 32-bit word of the wire (little-endian bytes); the
 // section holds ceil(n / 20) words, elements past n encode as 0.
 __global__ void __launch_bounds__(256)
-sign_encode_t5_kernel(const float *__restrict__ v, int64_t n, uint32_t *__restrict__ packed)
+sign_encode_t5_kernel(const float *__restrict__ v, int64_t n, uint32_t *__restrict__ packed, const Rider rider)
 {
     pdl_launch_dependents();
     const int64_t n_words = (n + 19) / 20;
     pdl_wait();
+    rider_run(rider, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);   // identity tensors ride along
     for (int64_t w = (int64_t)blockIdx.x * 256 + threadIdx.x; w < n_words; w += (int64_t)gridDim.x * 256) {
         const int64_t i0 = w * 20;
         float x[20];
@@ -865,7 +873,7 @@ sign_encode_t5_kernel(const float *__restrict__ v, int64_t n, uint32_t *__restri
 template <int U_>
 __global__ void __launch_bounds__(256)
 sign_decode_reduce_t5_kernel(const uint32_t *__restrict__ packed, int64_t user_stride_words, int n_users_rt,
-                             int64_t n, float inv_u, float div_u, int accumulate, float *__restrict__ out)
+                             int64_t n, float inv_u, float div_u, int accumulate, float *__restrict__ out, const Rider rider)
 {
     __shared__ float4 s_t[8][160];   // per warp: 640 floats
     pdl_launch_dependents();
@@ -875,6 +883,7 @@ sign_decode_reduce_t5_kernel(const uint32_t *__restrict__ packed, int64_t user_s
     const int64_t n_words = (n + 19) / 20;
     const bool aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
     pdl_wait();
+    rider_run(rider, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);   // identity tensors ride along
     for (int64_t tile = (int64_t)blockIdx.x * 8 + warp; tile < n_tiles; tile += (int64_t)gridDim.x * 8) {
         const int64_t e0 = tile * 640;
         const int64_t w = tile * 32 + lane;
@@ -936,7 +945,8 @@ sign_decode_reduce_t5_kernel(const uint32_t *__restrict__ packed, int64_t user_s
 int sign_encode_t5(const float *grad, int64_t n, uint32_t *packed, cudaStream_t st)
 {
     if (n == 0) return GQ_OK;
-    GQ_CUDA(launch_pdl(sign_encode_t5_kernel, dim3(grid_for((n + 19) / 20, 256, 16)), dim3(256), 0, st, grad, n, packed));
+    const Rider rider = take_rider();   // a pending identity copy rides in this launch
+    GQ_CUDA(launch_pdl(sign_encode_t5_kernel, dim3(grid_for((n + 19) / 20, 256, 16)), dim3(256), 0, st, grad, n, packed, rider));
     GQ_LAUNCH_CHECK("sign_encode_t5");
     return GQ_OK;
 }
@@ -948,8 +958,9 @@ int sign_decode_reduce_t5(const uint32_t *packed, int64_t user_stride_words, int
     float inv_u, div_u;
     mean_factors(mean, n_users, &inv_u, &div_u);
     const int grid = grid_for((n + 639) / 640, 8, 8);
+    const Rider rider = take_rider();   // a pending identity reduction rides in this launch
 #define GQ_S(UU) GQ_CUDA(launch_pdl(sign_decode_reduce_t5_kernel<UU>, dim3(grid), dim3(256), 0, st, packed, user_stride_words, \
-                                    n_users, n, inv_u, div_u, accumulate, out))
+                                    n_users, n, inv_u, div_u, accumulate, out, rider))
     if (n_users == 1) GQ_S(1);
     else if (n_users == 2) GQ_S(2);
     else if (n_users == 4) GQ_S(4);
@@ -964,11 +975,12 @@ int sign_decode_reduce_t5(const uint32_t *packed, int64_t user_stride_words, int
 // wire -- four 16-byte loads in flight per thread and a coalesced 128-byte store per warp instead of 32
 // single bytes (21.0 -> see DESIGN.md section 8)
 __global__ void __launch_bounds__(256)
-sign_encode_words_kernel(const float *__restrict__ v, int64_t n, uint32_t *__restrict__ packed)
+sign_encode_words_kernel(const float *__restrict__ v, int64_t n, uint32_t *__restrict__ packed, const Rider rider)
 {
     pdl_launch_dependents();
     const int64_t n_words = n / 16;   // whole words; the ragged tail goes through sign_encode_kernel
     pdl_wait();
+    rider_run(rider, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);   // identity tensors ride along
     for (int64_t w = (int64_t)blockIdx.x * 256 + threadIdx.x; w < n_words; w += (int64_t)gridDim.x * 256) {
         float4 t[4];
 #pragma unroll
@@ -990,8 +1002,9 @@ int sign_encode(const float *grad, int64_t n, float *out_f32, uint8_t *packed, c
     if (n == 0) return GQ_OK;
     if (!out_f32 && packed && ((uintptr_t)packed & 3) == 0 && n >= 16) {
         const int64_t n_words = n / 16;
+        const Rider rider = take_rider();   // a pending identity copy rides in this launch
         GQ_CUDA(launch_pdl(sign_encode_words_kernel, dim3(grid_for(n_words, 256, 16)), dim3(256), 0, st, grad, n,
-                           reinterpret_cast<uint32_t *>(packed)));
+                           reinterpret_cast<uint32_t *>(packed), rider));
         const int64_t done = n_words * 16;
         if (done < n)   // at most 15 elements
             sign_encode_kernel<<<1, 32, 0, st>>>(grad + done, n - done, nullptr, packed + done / 4);
@@ -1010,8 +1023,9 @@ int sign_decode_reduce(const uint8_t *packed, int64_t user_stride, int n_users, 
     float inv_u, div_u;
     mean_factors(mean, n_users, &inv_u, &div_u);
     const int grid = grid_for((n + 511) / 512, 8, 16);
+    const Rider rider = take_rider();   // a pending identity reduction rides in this launch
 #define GQ_S(UU) GQ_CUDA(launch_pdl(sign_decode_reduce_kernel<UU>, dim3(grid), dim3(256), 0, st, packed, user_stride, n_users, n, \
-                                    inv_u, div_u, accumulate, out))
+                                    inv_u, div_u, accumulate, out, rider))
     if (n_users == 1) GQ_S(1);
     else if (n_users == 2) GQ_S(2);
     else if (n_users == 4) GQ_S(4);
@@ -1035,6 +1049,7 @@ int gq_qsgd_encode(const float *grad, int64_t n, const int64_t *chunk_start, int
                    uint64_t philox_offset, float *norm, uint8_t *signs, int32_t *l, void *packed,
                    gq_stream_t stream)
 {
+    const Rider pending = take_rider();   // consumed first: an early error return must not leave it armed
     GQ_REQUIRE(n >= 0 && n_chunks >= 0, "negative size");
     GQ_REQUIRE(n_bit >= 1 && n_bit <= 14, "n_bit %d out of range 1..14", n_bit);
     GQ_REQUIRE(chunk_start || (dim >= 1 && n_chunks * (int64_t)dim == n),
@@ -1042,20 +1057,29 @@ int gq_qsgd_encode(const float *grad, int64_t n, const int64_t *chunk_start, int
     GQ_REQUIRE(n == 0 || (grad && norm), "null pointer");
     GQ_REQUIRE(packed || (signs && l), "need packed or (signs and l) outputs");
     GQ_REQUIRE(((uintptr_t)grad & 15) == 0, "gradient must be 16-byte aligned");
-    return qsgd_encode(grad, n, chunk_start, n_chunks, dim, n_bit, random, uniforms, philox_seed,
-                       philox_offset, norm, signs, l, packed, as_stream(stream));
+    set_rider(pending);
+    const int e = qsgd_encode(grad, n, chunk_start, n_chunks, dim, n_bit, random, uniforms, philox_seed,
+                              philox_offset, norm, signs, l, packed, as_stream(stream));
+    const Rider left = take_rider();
+    if (e) return e;
+    return launch_rider(left, as_stream(stream));   // no-op when the encode kernel carried it
 }
 
 int gq_qsgd_decode_reduce(const float *norm, const void *packed, int64_t user_stride_bytes, int n_users,
                           int64_t n, const int64_t *chunk_start, int64_t n_chunks, int dim, int n_bit,
                           int mean, int accumulate, float *out, gq_stream_t stream)
 {
+    const Rider pending = take_rider();
     GQ_REQUIRE(n >= 0 && n_users >= 1, "bad sizes");
     GQ_REQUIRE(n_bit >= 1 && n_bit <= 14, "n_bit %d out of range 1..14", n_bit);
     GQ_REQUIRE(chunk_start || (dim >= 1 && n_chunks * (int64_t)dim == n), "n != n_chunks * dim");
     GQ_REQUIRE(n == 0 || (norm && packed && out), "null pointer");
-    return qsgd_decode_reduce(norm, packed, user_stride_bytes, n_users, n, chunk_start, n_chunks, dim,
-                              n_bit, mean, accumulate, out, as_stream(stream));
+    set_rider(pending);
+    const int e = qsgd_decode_reduce(norm, packed, user_stride_bytes, n_users, n, chunk_start, n_chunks, dim,
+                                     n_bit, mean, accumulate, out, as_stream(stream));
+    const Rider left = take_rider();
+    if (e) return e;
+    return launch_rider(left, as_stream(stream));
 }
 
 int gq_qsgd_decode_unpacked(const float *norm, const uint8_t *signs, const int32_t *l, int64_t n,
@@ -1071,36 +1095,55 @@ int gq_qsgd_decode_unpacked(const float *norm, const uint8_t *signs, const int32
 
 int gq_sign_encode(const float *grad, int64_t n, float *out_f32, uint8_t *packed, gq_stream_t stream)
 {
+    const Rider pending = take_rider();
     GQ_REQUIRE(n >= 0 && (n == 0 || grad), "bad arguments");
     GQ_REQUIRE(out_f32 || packed, "need at least one output");
     GQ_REQUIRE(((uintptr_t)grad & 15) == 0, "gradient must be 16-byte aligned");
-    return sign_encode(grad, n, out_f32, packed, as_stream(stream));
+    set_rider(pending);
+    const int e = sign_encode(grad, n, out_f32, packed, as_stream(stream));
+    const Rider left = take_rider();
+    if (e) return e;
+    return launch_rider(left, as_stream(stream));
 }
 
 int gq_sign_decode_reduce(const uint8_t *packed, int64_t user_stride_bytes, int n_users, int64_t n,
                           int mean, int accumulate, float *out, gq_stream_t stream)
 {
+    const Rider pending = take_rider();
     GQ_REQUIRE(n >= 0 && n_users >= 1 && (n == 0 || (packed && out)), "bad arguments");
-    return sign_decode_reduce(packed, user_stride_bytes, n_users, n, mean, accumulate, out,
-                              as_stream(stream));
+    set_rider(pending);
+    const int e = sign_decode_reduce(packed, user_stride_bytes, n_users, n, mean, accumulate, out, as_stream(stream));
+    const Rider left = take_rider();
+    if (e) return e;
+    return launch_rider(left, as_stream(stream));
 }
 
 int64_t gq_sign_t5_bytes(int64_t n) { return n <= 0 ? 0 : (n + 19) / 20 * 4; }
 
 int gq_sign_encode_t5(const float *grad, int64_t n, void *packed, gq_stream_t stream)
 {
+    const Rider pending = take_rider();
     GQ_REQUIRE(n >= 0 && (n == 0 || (grad && packed)), "bad arguments");
     GQ_REQUIRE(((uintptr_t)grad & 15) == 0 && ((uintptr_t)packed & 3) == 0, "gradient 16-byte, wire 4-byte aligned");
-    return sign_encode_t5(grad, n, reinterpret_cast<uint32_t *>(packed), as_stream(stream));
+    set_rider(pending);
+    const int e = sign_encode_t5(grad, n, reinterpret_cast<uint32_t *>(packed), as_stream(stream));
+    const Rider left = take_rider();
+    if (e) return e;
+    return launch_rider(left, as_stream(stream));
 }
 
 int gq_sign_decode_reduce_t5(const void *packed, int64_t user_stride_bytes, int n_users, int64_t n, int mean,
                              int accumulate, float *out, gq_stream_t stream)
 {
+    const Rider pending = take_rider();
     GQ_REQUIRE(n >= 0 && n_users >= 1 && (n == 0 || (packed && out)), "bad arguments");
     GQ_REQUIRE(((uintptr_t)packed & 3) == 0 && (user_stride_bytes & 3) == 0, "wire sections are 4-byte aligned");
-    return sign_decode_reduce_t5(reinterpret_cast<const uint32_t *>(packed), user_stride_bytes / 4, n_users, n, mean,
-                                 accumulate, out, as_stream(stream));
+    set_rider(pending);
+    const int e = sign_decode_reduce_t5(reinterpret_cast<const uint32_t *>(packed), user_stride_bytes / 4, n_users, n, mean,
+                                        accumulate, out, as_stream(stream));
+    const Rider left = take_rider();
+    if (e) return e;
+    return launch_rider(left, as_stream(stream));
 }
 
 }  // extern "C"

@@ -448,10 +448,13 @@ class FusedPlan:
                     _lib.call("gq_f32_reduce_users", gp, 0, 1, g.n, 0, 0, base + g.raw_off, st)
 
     def _rider_pair(self, n_users=1):
-        """(identity group, HSQ group whose first kernel carries the identity tensors' copy /
-        reduction) or (None, None)."""
+        """(identity group, group whose first kernel carries the identity tensors' copy / reduction) or
+        (None, None).  Carriers: HSQ, and the one-launch sign / QSGD kernels (their C entry points consume
+        a pending gq_attach_f32_reduce; a path without a carrier kernel launches it on its own)."""
         ident = next((g for g in self.groups if g.kind == "identity" and g.n), None)
-        carrier = next((g for g in self.groups if g.kind == "hsq"), None)
+        # (the largest group: its kernel has the threads to spare -- riding in a group of a few chunks made
+        #  that 6 us launch a 60 us one)
+        carrier = max((g for g in self.groups if g.kind in ("hsq", "sign", "qsgd")), key=lambda g: g.n, default=None)
         if ident is None or carrier is None or n_users > 8:
             return None, None
         return ident, carrier
@@ -573,7 +576,7 @@ class FusedPlan:
                 k -= 1 if (v1 or g.n_seg > 1024 or g.n_bit > 7) else 2
             n += k
         ident, carrier = self._rider_pair()
-        if carrier is not None and carrier.n_bit != 32:   # the copy rides in the HSQ init / search kernel
+        if carrier is not None and (carrier.kind != "hsq" or carrier.n_bit != 32):   # the copy rides in the carrier's kernel
             n -= 1
         return n
 
@@ -582,7 +585,8 @@ class FusedPlan:
         for g in self.groups:
             n += (2 + n_users) if g.kind == "topk" else 1
         ident, carrier = self._rider_pair(n_users)
-        if (carrier is not None and carrier.dim == 16 and carrier.K == 256 and carrier.code_bytes == 1
-                and carrier.l_bytes == 1 and carrier.n_bit != 32):   # rides in the staged decode kernel
+        if carrier is not None and (carrier.kind != "hsq" or (
+                carrier.dim == 16 and carrier.K == 256 and carrier.code_bytes == 1
+                and carrier.l_bytes == 1 and carrier.n_bit != 32)):   # rides in the (staged) decode kernel
             n -= 1
         return n
