@@ -38,10 +38,11 @@ __device__ __forceinline__ uint32_t key_of(float x) { return __float_as_uint(x) 
 // histograms
 __global__ void topk_setup_kernel(const int64_t *__restrict__ seg_start, const int64_t *__restrict__ k,
                                   int n_seg, int64_t *__restrict__ tile_prefix, int64_t *__restrict__ run_prefix,
-                                  TopkState *__restrict__ state, uint32_t *__restrict__ hist)
+                                  TopkState *__restrict__ state, uint32_t *__restrict__ hist, const Rider rider)
 {
     pdl_launch_dependents();
     pdl_wait();
+    rider_run(rider, (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);   // identity tensors ride along
     if (blockIdx.x == 0 && threadIdx.x < 32) {
         // exclusive prefix sums of the tensors' tile / run counts: one warp, 32 tensors per step
         const int lane = threadIdx.x;
@@ -499,8 +500,9 @@ int topk_select(const float *grad, int64_t n, const int64_t *seg_start, const in
     // (one warp per tile, a chain of dependent loads per tile: as many warps in flight as fit)
     const int grid_lists = (int)(warp_blocks < 2 * cap ? warp_blocks : 2 * cap);
     const int grid_setup = (int)std::min<int64_t>(((int64_t)n_seg * kBins + 255) / 256, cap);
+    const Rider rider = take_rider();   // a pending identity copy rides in the first launch
     GQ_CUDA(launch_pdl(topk_setup_kernel, dim3(grid_setup), dim3(256), 0, st, seg_start, k, n_seg, w.tile_prefix,
-                       w.run_prefix, w.state, w.hist));
+                       w.run_prefix, w.state, w.hist, rider));
     GQ_CUDA(launch_pdl(topk_hist0_kernel, dim3(grid_runs), dim3(256), 0, st, grad, seg_start, (const int64_t *)w.run_prefix,
                        n_seg, (const TopkState *)w.state, w.hist));
     GQ_CUDA(launch_pdl(topk_scan_kernel<0>, dim3(n_seg), dim3(256), 0, st, w.hist, w.state));
@@ -526,8 +528,9 @@ int topk_select(const float *grad, int64_t n, const int64_t *seg_start, const in
 
 // ------------------------------------------------------- scatter + reduce ---
 __global__ void __launch_bounds__(256)
-fill_kernel(float *__restrict__ out, int64_t n, float val)
+fill_kernel(float *__restrict__ out, int64_t n, float val, const Rider rider)
 {
+    rider_run(rider, (int64_t)blockIdx.x * 256 + threadIdx.x, (int64_t)gridDim.x * 256);   // identity tensors ride along
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256)
         out[i] = val;
 }
@@ -562,7 +565,8 @@ int topk_scatter_reduce(const int32_t *idx, const float *val, int64_t user_strid
     if (n == 0) return GQ_OK;
     // mean with accumulate: out + (sum)/U needs a scratch-free formulation only when U == 1
     if (!accumulate) {
-        fill_kernel<<<grid_for(n), 256, 0, st>>>(out, n, 0.0f);
+        const Rider rider = take_rider();   // a pending identity reduction rides in the fill
+        fill_kernel<<<grid_for(n), 256, 0, st>>>(out, n, 0.0f, rider);
     }
     for (int u = 0; u < n_users; ++u) {
         const int32_t *iu = reinterpret_cast<const int32_t *>(reinterpret_cast<const char *>(idx) + u * user_stride);
@@ -586,6 +590,7 @@ int gq_topk_select(const float *grad, int64_t n, const int64_t *seg_start, const
                    const int64_t *k_prefix, int n_seg, float *out_dense, int32_t *out_idx, float *out_val,
                    void *workspace, size_t workspace_bytes, gq_stream_t stream)
 {
+    const Rider pending = take_rider();   // consumed first: an early error return must not leave it armed
     GQ_REQUIRE(n >= 0 && n_seg >= 1, "bad sizes");
     GQ_REQUIRE(n < ((int64_t)1 << 31), "top-k group larger than 2^31 elements");
     GQ_REQUIRE(grad && seg_start && k, "null pointer");
@@ -595,19 +600,28 @@ int gq_topk_select(const float *grad, int64_t n, const int64_t *seg_start, const
         set_error("workspace too small: %zu < %zu", workspace_bytes, topk_workspace_bytes(n, n_seg));
         return GQ_ERR_WORKSPACE;
     }
-    return topk_select(grad, n, seg_start, k, k_prefix, n_seg, out_dense, out_idx, out_val, workspace,
-                       as_stream(stream));
+    set_rider(pending);
+    const int e = topk_select(grad, n, seg_start, k, k_prefix, n_seg, out_dense, out_idx, out_val, workspace,
+                              as_stream(stream));
+    const Rider left = take_rider();
+    if (e) return e;
+    return launch_rider(left, as_stream(stream));   // no-op when the setup kernel carried it
 }
 
 int gq_topk_scatter_reduce(const int32_t *idx, const float *val, int64_t user_stride_bytes, int n_users,
                            int64_t k_total, int64_t n, int mean, int accumulate, float *out,
                            gq_stream_t stream)
 {
+    const Rider pending = take_rider();
     GQ_REQUIRE(n >= 0 && k_total >= 0 && n_users >= 1, "bad sizes");
     GQ_REQUIRE(!(mean && accumulate && n_users > 1), "mean + accumulate is not defined for top-k scatter");
     GQ_REQUIRE(k_total == 0 || (idx && val), "null pointer");
-    return topk_scatter_reduce(idx, val, user_stride_bytes, n_users, k_total, n, mean, accumulate, out,
-                               as_stream(stream));
+    set_rider(pending);
+    const int e = topk_scatter_reduce(idx, val, user_stride_bytes, n_users, k_total, n, mean, accumulate, out,
+                                      as_stream(stream));
+    const Rider left = take_rider();
+    if (e) return e;
+    return launch_rider(left, as_stream(stream));
 }
 
 }  // extern "C"

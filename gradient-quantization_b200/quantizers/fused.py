@@ -449,12 +449,12 @@ class FusedPlan:
 
     def _rider_pair(self, n_users=1):
         """(identity group, group whose first kernel carries the identity tensors' copy / reduction) or
-        (None, None).  Carriers: HSQ, and the one-launch sign / QSGD kernels (their C entry points consume
+        (None, None).  Carriers: HSQ, the one-launch sign / QSGD kernels, top-k's setup / fill kernels (their C entry points consume
         a pending gq_attach_f32_reduce; a path without a carrier kernel launches it on its own)."""
         ident = next((g for g in self.groups if g.kind == "identity" and g.n), None)
         # (the largest group: its kernel has the threads to spare -- riding in a group of a few chunks made
         #  that 6 us launch a 60 us one)
-        carrier = max((g for g in self.groups if g.kind in ("hsq", "sign", "qsgd")), key=lambda g: g.n, default=None)
+        carrier = max((g for g in self.groups if g.kind in ("hsq", "sign", "qsgd", "topk")), key=lambda g: g.n, default=None)
         if ident is None or carrier is None or n_users > 8:
             return None, None
         return ident, carrier

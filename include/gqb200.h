@@ -152,7 +152,8 @@ int gq_f32_reduce_users_scattered(const float *in, const int64_t *user_byte_offs
 /* Attach a small gq_f32_reduce_users[_scattered] job (the identity tensors of a model: n_users = 1
  * copy at encode time, sum / mean over users at decode time) to the NEXT gq_hsq_encode,
  * gq_hsq_decode_reduce, gq_hsq_decode_reduce_scattered, gq_qsgd_encode, gq_qsgd_decode_reduce,
- * gq_sign_encode[_t5] or gq_sign_decode_reduce[_t5] call made by this host thread: it runs
+ * gq_sign_encode[_t5], gq_sign_decode_reduce[_t5], gq_topk_select or gq_topk_scatter_reduce call made by
+ * this host thread: it runs
  * inside that call's first kernel (or, if that code path cannot carry it, in a launch of its own
  * issued by that call) instead of costing a separate ~3 us launch.  Same arguments and results as
  * gq_f32_reduce_users (user_byte_offsets == NULL: user u at in + u * user_stride_bytes) /
