@@ -203,3 +203,21 @@ def test_sign_wire_containers_in_the_plan_layout():
     assert p5.wire_bytes() == p2.wire_bytes() - g2.wire_bytes + g5.wire_bytes
     assert 0.79 < g5.wire_bytes / g2.wire_bytes < 0.81            # 1.6 instead of 2 bits per element
     assert p5.record_bytes % 256 == 0 and p5.tensor_off == p2.tensor_off
+
+
+def test_identity_tensors_ride_in_the_largest_group_of_every_codec():
+    """The copy / reduction of the tensors with <= 1000 elements is attached to the largest compressed group
+    (its kernel has the threads to spare); more than 8 users: a launch of its own."""
+    shapes = resnet50_shapes()
+    for Comp, kw in ((gq_b200.NearestNeighborCompressor, {}), (gq_b200.QSGDCompressor, dict(c_dim=128, n_bit=2)),
+                     (gq_b200.SignSGDCompressor, {}), (gq_b200.TopKSparsificationCompressor, dict(cr=100))):
+        plan = FusedPlan(Comp, shapes, make_args(**kw), torch.device("cpu"), 2)
+        ident, carrier = plan._rider_pair()
+        assert ident is not None and ident.kind == "identity" and ident.n == 22410
+        compressed = [g for g in plan.groups if g.kind != "identity"]
+        assert carrier is max(compressed, key=lambda g: g.n)
+        assert plan._rider_pair(n_users=9) == (None, None)
+    qs = FusedPlan(gq_b200.QSGDCompressor, shapes, make_args(c_dim=128, n_bit=2), torch.device("cpu"), 2)
+    assert [g.key for g in qs.groups if g.kind == "qsgd"] == [192, 128] and qs._rider_pair()[1].key == 128
+    ide = FusedPlan(gq_b200.IdenticalCompressor, shapes, make_args(), torch.device("cpu"), 2)
+    assert ide._rider_pair() == (None, None)
